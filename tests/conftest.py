@@ -1,0 +1,14 @@
+"""pytest configuration: registers the `gpu` marker and puts the product package (the `lsi` drop-in, which lives
+under layered-scene-inference_b200/) and the repo root on sys.path."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'layered-scene-inference_b200')
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
