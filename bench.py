@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- rendered views/sec of the B200-native LDI renderer at BASELINE.json's headline configuration
+(256x832, 4-layer LDI, batch 64 per GPU), with the splat kernel's HBM roofline, the reference CPU path timed on
+the box's host cores, and the end-to-end (host buffers in/out) number.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" = one pass of the renderer hot path (lsi.geometry.ldi.forward_splat, compose_layers=True,
+trg_downsampling=1: project + z-weight + bilinear forward splat + soft-z compose) over one batch of B synthetic
+LDIs already resident in HBM.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, 'layered-scene-inference_b200'), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+H, W, L, B_PER_GPU = 256, 832, 4, 64
+MAX_DISP, BG_DISP, ZBUF_SCALE, DS = 0.4, 1e-3, 50.0, 1.0      # kitti constants, ldi_enc_dec.py:421-425
+METRIC = 'rendered views/sec at 256x832x4-layer'
+WORKLOAD = ('KITTI-like 256x832, 4-layer LDI, batch %d per GPU: lsi.geometry.ldi.forward_splat '
+            '(compose_layers=True, trg_downsampling=1); renderer slice only -- the encoder-decoder CNN is not yet in '
+            'the step' % B_PER_GPU)
+
+
+def bytes_fwd_per_view(has_mask):
+    """reads tex(3)+disp(1)(+mask(1)) per source pixel per layer, writes img(3)+wts(1) per
+    target pixel (trg_disp is not requested on the training path)."""
+    n, nt = H * W, int(H * DS) * int(W * DS)
+    return 4 * ((5 if has_mask else 4) * L * n + 4 * nt)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def make_inputs(batch, seed):
+    """Synthetic KITTI-like LDIs: 8 procedurally generated scenes, tiled to the batch with a
+    per-copy disparity scale so that no two views scatter identically."""
+    from oracle import gen_inputs
+    uniq = min(batch, 8)
+    s = gen_inputs.scene(L, uniq, H, W, 'kitti', seed, MAX_DISP)
+    reps = (batch + uniq - 1) // uniq
+    out = {}
+    for k, v in s.items():
+        axis = 1 if k in ('tex', 'mask', 'disp') else 0
+        out[k] = np.concatenate([v] * reps, axis=axis)
+        out[k] = np.ascontiguousarray(out[k][:, :batch] if axis == 1 else out[k][:batch])
+    scale = (1.0 - 0.01 * (np.arange(batch) // uniq)).astype(np.float32)
+    out['disp'] = out['disp'] * scale[None, :, None, None, None]
+    return out
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU algorithm (TF-1.4 is not installable here, so this is the op-for-op
+    CPU restatement oracle/lsi_oracle.py, `kind: port`) on the host cores, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import lsi_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    views = 2                                    # bounded sample: 2 of the 64 views per step
+    s = make_inputs(views, 0)
+    ldi = tuple(torch.tensor(s[k]) for k in ('tex', 'mask', 'disp'))
+    cam = [torch.tensor(s[k]) for k in ('k_s', 'k_t', 'rot', 't')]
+    pc = O.pixel_coords(views, H, W)
+    kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        O.forward_splat(ldi, pc, *cam, **kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.forward_splat(ldi, pc, *cam, **kw)
+    dt = (time.perf_counter() - t0) / steps
+    v = views / dt
+    sample = '%d of %d views per step, %d steps, torch CPU %d threads' % (views, B_PER_GPU, steps, cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'views/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'views/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def cpu_baseline():
+    from oracle import lsi_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    views = 2
+    s = make_inputs(views, 0)
+    ldi = tuple(torch.tensor(s[k]) for k in ('tex', 'mask', 'disp'))
+    cam = [torch.tensor(s[k]) for k in ('k_s', 'k_t', 'rot', 't')]
+    pc = O.pixel_coords(views, H, W)
+    kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
+    O.forward_splat(ldi, pc, *cam, **kw)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+        O.forward_splat(ldi, pc, *cam, **kw)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {'value': views / dt, 'unit': 'views/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d of %d views x %d reps of oracle/lsi_oracle.forward_splat (reference decomposition: per layer 3 '
+                      'splats, per channel x 4 corners scatter-into-zeros + add), torch CPU fp32' % (views, B_PER_GPU, reps)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    from lsi import _b200
+    from lsi.geometry import ldi as ldi_utils
+    from lsi.nnutils import helpers
+    lib = _b200.lib()
+
+    B = B_PER_GPU
+    host = make_inputs(B, seed=rank)
+    has_mask = False                               # nets.py:205: masks are all ones on the training path
+    tex, disp = torch.tensor(host['tex'], device=dev), torch.tensor(host['disp'], device=dev)
+    masks = torch.ones(L, B, H, W, 1, device=dev)
+    masks._lsi_all_ones = True
+    cam = [torch.tensor(host[k], device=dev) for k in ('k_s', 'k_t', 'rot', 't')]
+    pc = helpers.pixel_coords(B, H, W, device=dev)
+    kw = dict(compose_layers=True, trg_downsampling=DS, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
+
+    def step():
+        with torch.no_grad():
+            return ldi_utils.forward_splat((tex, masks, disp), pc, *cam, **kw)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = _b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _b200.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if dist is not None:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # --- roofline of the dominant kernel (forward splat), timed live with CUDA events on its stream -------------
+    lib.lsi_b200_kernel_timing_enable(1)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    kms, kn = (ctypes.c_double * 4)(), (ctypes.c_int * 4)()
+    _b200.call('lsi_b200_kernel_timing_collect', ctypes.cast(kms, ctypes.c_void_p), ctypes.cast(kn, ctypes.c_void_p))
+    lib.lsi_b200_kernel_timing_enable(0)
+    peak, peak_src = load_peaks()
+    n_src, n_trg = H * W, int(H * DS) * int(W * DS)
+    splat_bytes_per_step = 4.0 * (5 if has_mask else 4) * L * n_src * B      # the splat kernel's algorithmic reads
+    splat_ms_per_step = kms[0] / args.steps
+    norm_ms_per_step = kms[1] / args.steps
+    achieved = splat_bytes_per_step / (splat_ms_per_step * 1e-3) / 1e9
+    step_bytes = bytes_fwd_per_view(has_mask) * B
+    roofline = {'bound': 'hbm', 'kernel': 'splat_fwd (forward splat; launches per step: %d)' % (kn[0] // args.steps),
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+                'traffic': None, 'algorithmic_bytes_per_step': splat_bytes_per_step,
+                'kernel_ms_per_step': splat_ms_per_step, 'normalize_ms_per_step': norm_ms_per_step,
+                'step_achieved_gbs': step_bytes / (ms_per_step * 1e-3) / 1e9,
+                'step_frac': step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    # --- end to end through the C ABI with HOST buffers: H2D of the LDI + cameras, render, D2H of img + wts --------
+    pin = {k: torch.tensor(host[k]).pin_memory() for k in ('tex', 'disp', 'k_s', 'k_t', 'rot', 't')}
+    out_img = torch.empty(1, B, int(H * DS), int(W * DS), 3).pin_memory()
+    out_wts = torch.empty(1, B, int(H * DS), int(W * DS), 1).pin_memory()
+    desc = _b200.SplatDesc(L, B, H, W, int(H * DS), int(W * DS), DS, BG_DISP, MAX_DISP, ZBUF_SCALE, 1, 0, 3, 1, 1, 0)
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        _b200.call('lsi_b200_forward_splat_host', desc, hp(pin['tex']), None, hp(pin['disp']), hp(pin['k_s']),
+                   hp(pin['k_t']), hp(pin['rot']), hp(pin['t']), hp(out_img), hp(out_wts), None)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = tt.item()
+    h2d = sum(pin[k].numel() * 4 for k in pin)
+    d2h = (out_img.numel() + out_wts.numel()) * 4
+    e2e = {'value': world * B / e2e_s, 'unit': 'views/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'ms_per_step': e2e_s * 1e3, 'api': 'lsi_b200_forward_splat_host (pinned host buffers)'}
+
+    cpu = cpu_baseline() if (rank == 0 and world == 1) else None
+    if rank == 0:
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': 'views/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'h': H, 'w': W, 'layers': L, 'batch_per_gpu': B, 'global_batch': world * B,
+                       'parallelism': 'dp%d (independent views per rank, no data-path collective)' % world,
+                       'l2_policy': 'inputs (%.2f GB per step) exceed the 126 MB L2' % (splat_bytes_per_step / 1e9)},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

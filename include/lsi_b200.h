@@ -1,0 +1,165 @@
+/* lsi_b200.h -- C ABI of the B200-native LDI view-synthesis hot path.
+ *
+ * Drop-in boundary for the renderer/loss slice of google/layered-scene-inference.  The reference has no
+ * FFI of its own (it is TF-1 graph Python); the functions below are what the Python call sites of
+ *   lsi/geometry/ldi.py, lsi/geometry/sampling.py, lsi/geometry/projection.py, lsi/nnutils/helpers.py,
+ *   lsi/loss/loss.py and the loss glue of ldi_enc_dec.py
+ * bind to (through ctypes, see layered-scene-inference_b200/lsi/_b200.py and INTEGRATION.md).  Each entry
+ * point cites the reference interface (file:line under the reference tree) it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer (fp32, contiguous) unless its name
+ *    ends in `_host`; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *  - images NHWC [B,H,W,C]; LDI tensors layer-first [L,B,H,W,C]; pixel centres at +0.5; intrinsics [B,3,3]
+ *    row-major; translations [B,3] (the reference's [B,3,1]).
+ *  - purely functional: inputs are never written; outputs/workspaces are caller-allocated.
+ *  - return value: 0 on success, LSI_B200_EINVAL (-1) for a rejected argument, LSI_B200_ECUDA (-2) for a CUDA
+ *    error; lsi_b200_last_error() gives the message (thread-local).  There is NO CPU fallback: without a
+ *    CUDA device every compute entry point fails with LSI_B200_ECUDA.
+ *  - all launches are asynchronous on `stream`; nothing here synchronises except the *_host entry points.
+ */
+#ifndef LSI_B200_H_
+#define LSI_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LSI_B200_API __attribute__((visibility("default")))
+#else
+#define LSI_B200_API
+#endif
+
+#define LSI_B200_OK 0
+#define LSI_B200_EINVAL (-1)
+#define LSI_B200_ECUDA (-2)
+
+LSI_B200_API int lsi_b200_version(void);
+LSI_B200_API const char* lsi_b200_last_error(void);
+/* Number of this library's kernels launched since load (bench.py's `gpu_launches`). */
+LSI_B200_API unsigned long long lsi_b200_launch_count(void);
+
+/* Measurement aid (bench.py's roofline): when enabled, CUDA events on the launching stream bracket every launch
+ * of the renderer kernels.  collect() waits for them and returns, per kernel kind (0 = forward splat,
+ * 1 = normalise/compose, 2 = backward target stage, 3 = backward source stage), the summed milliseconds and the
+ * launch count since the last collect.  Arrays of 4. */
+LSI_B200_API int lsi_b200_kernel_timing_enable(int on);
+LSI_B200_API int lsi_b200_kernel_timing_collect(double* ms_by_kind, int* launches_by_kind);
+
+/* ------------------------------------------------------------------------------------------------
+ * Renderer: lsi/geometry/ldi.py:71-182 forward_splat (+ projection.py:71-86, helpers.py:82-85,116-137,
+ * 180-193, sampling.py:171-313 fused inside).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lsi_b200_splat_desc {
+  int n_layers, batch, h_s, w_s, h_t, w_t;     /* h_t = h_s*trg_downsampling (ldi.py:113-114)               */
+  float trg_downsampling;                      /* ldi.py:139                                               */
+  float bg_layer_disp, max_disp, zbuf_scale;   /* ldi.py:115,145                                           */
+  int compose_layers;                          /* ldi.py:167-171 ; nl_out = compose ? 1 : n_layers          */
+  int compute_trg_disp;                        /* ldi.py:179-182                                           */
+  /* element strides between consecutive pixels of one (layer,batch) image: 3/1/1 for the reference's
+   * separate tex/disp/mask tensors, 4/4 when tex and disp are views into the packed [L,B,H,W,4] head
+   * output (nets.py:204).  (layer,batch) images must be densely packed: image stride = h_s*w_s*px_stride. */
+  int tex_px_stride, disp_px_stride, mask_px_stride;
+  int variant;                                 /* 0 = default; 1 = plain global-atomic kernel (ablation)   */
+} lsi_b200_splat_desc;
+
+/* src->trg (inverse==0, projection.py:71-86) or trg->src (inverse!=0, projection.py:89-106) 4x4 matrices.
+ * k_s,k_t,rot: [B,3,3]; t: [B,3]; out: [B,4,4] row-major. */
+LSI_B200_API int lsi_b200_projection_matrix(const float* k_s, const float* k_t, const float* rot, const float* t, int batch,
+                               int inverse, float* out, void* stream);
+
+/* Scratch bytes needed by lsi_b200_forward_splat / _backward for this descriptor. */
+LSI_B200_API size_t lsi_b200_forward_splat_workspace_bytes(const lsi_b200_splat_desc* d);
+LSI_B200_API size_t lsi_b200_forward_splat_backward_workspace_bytes(const lsi_b200_splat_desc* d);
+
+/* ldi.py:71-182.  tex [L,B,H,W,3], mask [L,B,H,W,1] (NULL = all ones, nets.py:205), disp [L,B,H,W,1];
+ * pixel_coords [B,H,W,3] or NULL for the standard (x+0.5,y+0.5,1) grid of helpers.py:88-113;
+ * focal_disps [B] or NULL (ldi.py:131-132,142-143).
+ * Outputs: trg_img [nl_out,B,Ht,Wt,3], trg_wts [nl_out,B,Ht,Wt,1], trg_disp [nl_out,B,Ht,Wt,1] (required iff
+ * compute_trg_disp).  layer_acc (optional, [L,B,Ht,Wt,2]) keeps the per-layer (sum w, sum w*d) accumulators
+ * that the backward of trg_disp needs. */
+LSI_B200_API int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float* tex, const float* mask, const float* disp,
+                           const float* pixel_coords, const float* k_s, const float* k_t, const float* rot,
+                           const float* t, const float* focal_disps, float* trg_img, float* trg_wts,
+                           float* trg_disp, float* layer_acc, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Gradient of the above w.r.t. tex / mask / disp (what TF autodiff gives train_utils.py:113); gather form,
+ * atomic-free.  trg_img/trg_wts are the saved forward outputs; g_img/g_wts/g_disp are the upstream gradients
+ * (any may be NULL = zero; g_disp needs layer_acc).  d_mask may be NULL. */
+LSI_B200_API int lsi_b200_forward_splat_backward(const lsi_b200_splat_desc* d, const float* tex, const float* mask,
+                                    const float* disp, const float* pixel_coords, const float* k_s,
+                                    const float* k_t, const float* rot, const float* t, const float* focal_disps,
+                                    const float* trg_img, const float* trg_wts, const float* layer_acc,
+                                    const float* g_img, const float* g_wts, const float* g_disp, float* d_tex,
+                                    float* d_mask, float* d_disp, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+
+/* Same as lsi_b200_forward_splat but with HOST buffers (pinned or pageable): copies the inputs to the device,
+ * renders, copies trg_img/trg_wts(/trg_disp) back and synchronises.  The reference-facing end-to-end path that
+ * bench.py times as `e2e`.  Device scratch is owned by the library and reused across calls. */
+LSI_B200_API int lsi_b200_forward_splat_host(const lsi_b200_splat_desc* d, const float* tex_host, const float* mask_host,
+                                const float* disp_host, const float* k_s_host, const float* k_t_host,
+                                const float* rot_host, const float* t_host, float* trg_img_host,
+                                float* trg_wts_host, float* trg_disp_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampling primitives: lsi/geometry/sampling.py
+ * ---------------------------------------------------------------------------------------------- */
+/* sampling.py:171-254 splat: out = init + scatter-add of src at coords (bilinear, 4 corners, weights <= 1e-3
+ * dropped).  src [B,Hs,Ws,C], coords [B,Hs,Ws,2] (x,y), init/out [B,Ht,Wt,C]. */
+LSI_B200_API int lsi_b200_splat(const float* src, const float* coords, const float* init, float* out, int batch, int h_s,
+                   int w_s, int h_t, int w_t, int channels, void* stream);
+/* gradient: g [B,Ht,Wt,C] -> d_src [B,Hs,Ws,C], d_coords [B,Hs,Ws,2] (d_init == g). */
+LSI_B200_API int lsi_b200_splat_backward(const float* src, const float* coords, const float* g, float* d_src, float* d_coords,
+                            int batch, int h_s, int w_s, int h_t, int w_t, int channels, void* stream);
+/* sampling.py:41-132 bilinear (compose=True): imgs [B,Hs,Ws,C], coords [B,Ht,Wt,2] -> out [B,Ht,Wt,C]. */
+LSI_B200_API int lsi_b200_bilinear(const float* imgs, const float* coords, float* out, int batch, int h_s, int w_s, int h_t,
+                      int w_t, int channels, void* stream);
+/* gradient: d_imgs must be zero-filled by the caller (scatter-add), d_coords [B,Ht,Wt,2]. */
+LSI_B200_API int lsi_b200_bilinear_backward(const float* imgs, const float* coords, const float* g, float* d_imgs,
+                               float* d_coords, int batch, int h_s, int w_s, int h_t, int w_t, int channels,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses: lsi/loss/loss.py and the loss glue of ldi_enc_dec.py.  Scalars are device floats.
+ * `partials` is scratch of lsi_b200_loss_partials_count() floats.
+ * ---------------------------------------------------------------------------------------------- */
+LSI_B200_API size_t lsi_b200_loss_partials_count(void);
+
+/* loss.py:66-115 zbuffer_composition_loss.  tex [L,N,3], mask [L,N,1] (NULL = ones), disp [L,N,1], trg [N,3]
+ * with N = B*H*W pixels. */
+LSI_B200_API int lsi_b200_zbuf_composition_loss(const float* tex, const float* mask, const float* disp, const float* trg,
+                                   int n_layers, long long n_pixels, float bg_layer_disp, float max_disp,
+                                   float zbuf_scale, float* loss, float* partials, void* stream);
+LSI_B200_API int lsi_b200_zbuf_composition_loss_backward(const float* tex, const float* mask, const float* disp,
+                                            const float* trg, int n_layers, long long n_pixels,
+                                            float bg_layer_disp, float max_disp, float zbuf_scale,
+                                            const float* g_loss, float* d_tex, float* d_mask, float* d_disp,
+                                            void* stream);
+
+/* ldi_enc_dec.py:337-357: AREA-downsample gt [B,H,W,3] to Ht x Wt (integer box), mean_c |gt - render|,
+ * min over the nl layers of render [nl,B,Ht,Wt,3], crop round(Wt*bdry)/round(Ht*bdry), mean. */
+LSI_B200_API int lsi_b200_photo_loss(const float* render, const float* gt, int n_layers, int batch, int h, int w, int h_t,
+                        int w_t, float bdry_ignore, float* loss, float* partials, void* stream);
+LSI_B200_API int lsi_b200_photo_loss_backward(const float* render, const float* gt, int n_layers, int batch, int h, int w,
+                                 int h_t, int w_t, float bdry_ignore, const float* g_loss, float* d_render,
+                                 void* stream);
+
+/* ldi.py:47-68 disp_smoothness_loss on disp [L*B,H,W] and loss.py:48-63 decreasing_disp_loss on [L,N]. */
+LSI_B200_API int lsi_b200_disp_smoothness_loss(const float* disp, int n_images, int h, int w, float* loss, float* partials,
+                                  void* stream);
+LSI_B200_API int lsi_b200_disp_smoothness_loss_backward(const float* disp, int n_images, int h, int w, const float* g_loss,
+                                           float* d_disp, void* stream);
+LSI_B200_API int lsi_b200_decreasing_disp_loss(const float* disp, int n_layers, long long n_pixels, float* loss,
+                                  float* partials, void* stream);
+LSI_B200_API int lsi_b200_decreasing_disp_loss_backward(const float* disp, int n_layers, long long n_pixels,
+                                           const float* g_loss, float* d_disp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSI_B200_H_ */

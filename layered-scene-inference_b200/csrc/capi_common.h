@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/lsi_b200.h"
+
+namespace lsi {
+
+void set_error(const char* fmt, ...);
+void count_launch(unsigned n = 1);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace lsi
+
+#define LSI_REQUIRE(cond, ...)              \
+  do {                                      \
+    if (!(cond)) {                          \
+      lsi::set_error(__VA_ARGS__);          \
+      return LSI_B200_EINVAL;               \
+    }                                       \
+  } while (0)
+
+#define LSI_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      lsi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return LSI_B200_ECUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+#define LSI_LAUNCH_CHECK()                                                                    \
+  do {                                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) {                                                                 \
+      lsi::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return LSI_B200_ECUDA;                                                                  \
+    }                                                                                         \
+    lsi::count_launch();                                                                      \
+  } while (0)

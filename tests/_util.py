@@ -21,3 +21,24 @@ def rel_err(a, b):
 
 def t32(x, device='cpu'):
     return torch.tensor(np.asarray(x), dtype=torch.float32, device=device)
+
+
+def outlier_frac(a, b, tol=1e-4):
+    """Fraction of elements whose error exceeds tol * max|b|, and the max error relative to max|b|."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    d = np.abs(a - b) / scale
+    return float((d > tol).mean()), float(d.max())
+
+
+def assert_parity(a, b, tol=1e-4, frac=1e-4, cap=None, what=''):
+    """fp32 parity that is robust to the reference's own discontinuity: sampling.py:219-222 zeroes corner weights
+    <= 1e-3, so an fp32-ulp difference in a projected coordinate flips that comparison for ~1e-5 of the pixels and
+    produces isolated jumps (<= 1e-3 * local contrast in a rendered value).  The reference's own fp32 and fp64
+    evaluations differ like that (6 of 106,496 px > 5e-5 on the 128x416 config), so: all but `frac` of the elements
+    within `tol` (relative to the tensor's max), and -- for forward values -- nothing beyond `cap`."""
+    f, m = outlier_frac(a, b, tol)
+    assert f <= frac, '%s: %.3g of elements beyond %g (max %.3g)' % (what, f, tol, m)
+    if cap is not None:
+        assert m <= cap, '%s: max error %.3g beyond cap %g' % (what, m, cap)

@@ -1,0 +1,292 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C-ABI library
+(lsi/_lib/liblsi_b200.so) via the `lsi` mirror package; the checker is the CPU oracle / the golden fixtures
+generated from the reference's own sources.  Tolerance: BASELINE.json's "1e-4 relative fp32", measured as
+max|a-b| / max|b| per tensor (rel_err in tests/_util.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_parity, load_golden, rel_err, t32
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+FS_CASES = ['fs_synth_ds05', 'fs_synth_ds1', 'fs_kitti_ds1', 'fs_kitti_ds05', 'fs_focal']
+
+
+@pytest.fixture(scope='module')
+def lsi_mods():
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    from lsi import _b200
+    from lsi.geometry import ldi, projection, sampling
+    from lsi.loss import loss
+    from lsi.nnutils import helpers
+    _b200.lib()
+    return dict(b200=_b200, ldi=ldi, projection=projection, sampling=sampling, loss=loss, helpers=helpers)
+
+
+def _cuda_case(g):
+    c = lambda k: t32(g['in_' + k], 'cuda')
+    kw = dict(trg_downsampling=float(g['in_ds']), bg_layer_disp=float(g['in_bg']), max_disp=float(g['in_max_disp']),
+              zbuf_scale=float(g['in_scale']))
+    if 'in_focal' in g:
+        kw['focal_disps'] = c('focal')
+    return c, kw
+
+
+def _grad_bar(g, key):
+    """The reference's own fp32 result is only this close to its fp64 evaluation; never ask for less noise than
+    1e-4, allow the larger of the two."""
+    return max(TOL, 1.5 * rel_err(g[key + '_f32'], g[key + '_f64']))
+
+
+@pytest.mark.parametrize('name', FS_CASES)
+@pytest.mark.parametrize('comp', ['c', 'i'])
+def test_forward_splat_golden(lsi_mods, name, comp):
+    g = load_golden(name)
+    c, kw = _cuda_case(g)
+    L, B, H, W, _ = g['in_tex'].shape
+    leaves = [c(k).requires_grad_(True) for k in ('tex', 'mask', 'disp')]
+    pc = lsi_mods['helpers'].pixel_coords(B, H, W)
+    img, wts, dsp = lsi_mods['ldi'].forward_splat(tuple(leaves), pc, c('k_s'), c('k_t'), c('rot'), c('t'),
+                                                  compose_layers=(comp == 'c'), compute_trg_disp=True, **kw)
+    for out, key in ((img, 'img_'), (wts, 'wts_'), (dsp, 'disp_')):
+        assert rel_err(out.detach().cpu(), g[key + comp + '_f64']) < TOL, key
+        assert rel_err(out.detach().cpu(), g[key + comp + '_f32']) < TOL, key
+    # gradient of <img, G> (what training uses), then of all three outputs
+    s = (img * c('g_img_' + comp)).sum()
+    grads = torch.autograd.grad(s, leaves, retain_graph=True)
+    for nme, gr in zip(('tex', 'mask', 'disp'), grads):
+        key = 'd%s_img_%s' % (nme, comp)
+        assert rel_err(gr.cpu(), g[key + '_f64']) < _grad_bar(g, key), key
+    s = s + (wts * c('g_wts_' + comp)).sum() + (dsp * c('g_disp_' + comp)).sum()
+    grads = torch.autograd.grad(s, leaves)
+    for nme, gr in zip(('tex', 'mask', 'disp'), grads):
+        key = 'd%s_all_%s' % (nme, comp)
+        assert rel_err(gr.cpu(), g[key + '_f64']) < _grad_bar(g, key), key
+
+
+@pytest.mark.parametrize('name', ['fs_synth_ds05', 'fs_kitti_ds1'])
+def test_forward_splat_input_forms_agree(lsi_mods, name):
+    """Explicit pixel_coords tensor, explicit all-ones mask, packed (stride-4) tex/disp views and the plain
+    global-atomic variant must all give the default path's result."""
+    g = load_golden(name)
+    c, kw = _cuda_case(g)
+    L, B, H, W, _ = g['in_tex'].shape
+    ldi, helpers = lsi_mods['ldi'], lsi_mods['helpers']
+    cam = (c('k_s'), c('k_t'), c('rot'), c('t'))
+    tex, mask, disp = c('tex'), c('mask'), c('disp')
+    pc = helpers.pixel_coords(B, H, W)
+    ref = ldi.forward_splat((tex, mask, disp), pc, *cam, compute_trg_disp=True, **kw)
+    alt = ldi.forward_splat((tex, mask, disp), pc.as_subclass(torch.Tensor).clone(), *cam, compute_trg_disp=True, **kw)
+    for a, b in zip(ref, alt):
+        assert rel_err(a.cpu(), b.cpu()) < 1e-6
+    packed = torch.cat([tex, disp], dim=-1)           # [L,B,H,W,4] like the head output (nets.py:204)
+    alt = ldi.forward_splat((packed[..., :3], mask, packed[..., 3:]), pc, *cam, compute_trg_disp=True, **kw)
+    for a, b in zip(ref, alt):
+        assert rel_err(a.cpu(), b.cpu()) < 1e-6
+    alt = ldi.forward_splat((tex, mask, disp), pc, *cam, compute_trg_disp=True, _variant=1, **kw)
+    for a, b in zip(ref, alt):
+        assert rel_err(a.cpu(), b.cpu()) < 1e-5
+    ones = torch.ones_like(mask)
+    a = ldi.forward_splat((tex, ones, disp), pc, *cam, **kw)
+    ones._lsi_all_ones = True
+    b = ldi.forward_splat((tex, ones, disp), pc, *cam, **kw)
+    assert rel_err(a[0].cpu(), b[0].cpu()) < 1e-6
+
+
+def test_primitives_golden(lsi_mods):
+    g = load_golden('primitives')
+    sampling, projection, helpers = lsi_mods['sampling'], lsi_mods['projection'], lsi_mods['helpers']
+    cu = lambda k: t32(g[k], 'cuda')
+    src, coords, init = cu('in_src').requires_grad_(True), cu('in_coords').requires_grad_(True), cu('in_init').requires_grad_(True)
+    init_before = init.detach().clone()
+    out = sampling.splat(src, coords, init)
+    assert torch.equal(init.detach(), init_before)                       # functional (sampling.py:283)
+    assert rel_err(out.detach().cpu(), g['splat_f64']) < TOL
+    gs, gc, gi = torch.autograd.grad((out * cu('in_g')).sum(), [src, coords, init])
+    assert rel_err(gs.cpu(), g['splat_dsrc_f64']) < TOL
+    assert rel_err(gc.cpu(), g['splat_dcoords_f64']) < TOL
+    assert rel_err(gi.cpu(), g['splat_dinit_f64']) < TOL
+    img, c2 = cu('in_img').requires_grad_(True), cu('in_coords').requires_grad_(True)
+    out = sampling.bilinear(img, c2)
+    assert rel_err(out.detach().cpu(), g['bilinear_f64']) < TOL
+    gi2, gc2 = torch.autograd.grad((out * cu('in_gb')).sum(), [img, c2])
+    assert rel_err(gi2.cpu(), g['bilinear_dimg_f64']) < TOL
+    assert rel_err(gc2.cpu(), g['bilinear_dcoords_f64']) < TOL
+    im5 = torch.stack([cu('in_img'), cu('in_img').flip(0)])
+    c5 = torch.stack([cu('in_coords'), cu('in_coords') * 0.9])
+    assert rel_err(sampling.bilinear_wrapper(im5, c5).cpu(), g['bilinear_wrapper_f64']) < TOL
+    cam = [cu('in_' + k) for k in ('k_s', 'k_t', 'rot', 't')]
+    fwd = projection.forward_projection_matrix(*cam)
+    inv = projection.inverse_projection_matrix(*cam)
+    assert rel_err(fwd.cpu(), g['proj_fwd_f64']) < 1e-6
+    assert rel_err(inv.cpu(), g['proj_inv_f64']) < 1e-6
+    assert torch.equal(fwd[:, 3].cpu(), torch.tensor([[0.0, 0, 0, 1]] * 2))
+    B, H, W, _ = g['in_d_src'].shape
+    dm = projection.disocclusion_mask(cu('in_d_src'), cu('in_d_trg'), helpers.pixel_coords(B, H, W), fwd, thresh=0.05)
+    assert (dm.cpu().numpy() != g['disocc_f64']).mean() < 0.02           # threshold compare: allow boundary flips
+    assert rel_err(helpers.zbuffer_weights(cu('in_zbw'), 50).cpu(), g['zbw50_f64']) < 1e-5
+    assert rel_err(helpers.soft_z_buffering(cu('in_lm'), cu('in_ld'), 0.4).cpu(), g['softz_f64']) < 1e-5
+    assert np.array_equal(helpers.enforce_bg_occupied(cu('in_lm')).cpu().numpy(), g['bg_occ_f32'])
+
+
+@pytest.mark.parametrize('name', ['loss_synth', 'loss_kitti'])
+def test_view_synthesis_loss_golden(lsi_mods, name):
+    import types
+    g = load_golden(name)
+    loss, helpers = lsi_mods['loss'], lsi_mods['helpers']
+    names = ('tex_s', 'mask_s', 'disp_s', 'tex_t', 'mask_t', 'disp_t')
+    leaves = [t32(g['in_' + k], 'cuda').requires_grad_(True) for k in names]
+    opts = types.SimpleNamespace(**{k[4:]: float(v) for k, v in g.items() if k.startswith('opt_')})
+    B, H, W, _ = g['in_img_s'].shape
+    cu = lambda k: t32(g['in_' + k], 'cuda')
+    total, parts = loss.view_synthesis_loss(tuple(leaves[:3]), tuple(leaves[3:]), cu('img_s'), cu('img_t'),
+                                            helpers.pixel_coords(B, H, W), cu('k_s'), cu('k_t'), cu('rot'), cu('t'), opts)
+    assert abs(total.item() - float(g['total_f64'])) < TOL * abs(float(g['total_f64']))
+    for k, gk in (('self_cons', 'self_cons'), ('indep_splat', 'indep_splat'), ('compose_splat', 'compose_splat'),
+                  ('disp_smoothness', 'smooth'), ('incr_depth', 'incr')):
+        assert abs(float(parts[k]) - float(g[gk + '_f64'])) <= TOL * max(abs(float(g[gk + '_f64'])), 1e-6), k
+    for nme, gr in zip(names, torch.autograd.grad(total, leaves)):
+        assert rel_err(gr.cpu(), g['d%s_f64' % nme]) < _grad_bar(g, 'd' + nme), nme
+    tex, mask, disp = (x.detach().requires_grad_(True) for x in leaves[:3])
+    zcl = loss.zbuffer_composition_loss(tex, mask, disp, cu('img_s'), bg_layer_disp=opts.bg_layer_disp,
+                                        max_disp=opts.max_disp, zbuf_scale=opts.zbuf_scale)
+    assert abs(zcl.item() - float(g['zcl_f64'])) < TOL * abs(float(g['zcl_f64']))
+    for nme, gr in zip(('tex', 'mask', 'disp'), torch.autograd.grad(zcl, [tex, mask, disp])):
+        assert rel_err(gr.cpu(), g['zcl_d%s_f64' % nme]) < TOL, nme
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded random inputs against the CPU oracle at sizes it finishes in seconds (BASELINE configs 1-3 shapes)
+# ---------------------------------------------------------------------------------------------------
+def _scene(L, B, H, W, cam, seed, max_disp):
+    from oracle import gen_inputs
+    return gen_inputs.scene(L, B, H, W, cam, seed, max_disp)
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(L=1, B=1, H=64, W=64, cam='identity', ds=1, bg=0.2, max_disp=1.0, scale=50),        # BASELINE config 1
+    dict(L=2, B=2, H=128, W=416, cam='kitti', ds=1, bg=1e-3, max_disp=0.4, scale=50),        # config 2 (B cut to 2)
+    dict(L=2, B=2, H=128, W=416, cam='kitti', ds=0.5, bg=1e-3, max_disp=0.4, scale=50),
+    dict(L=3, B=2, H=256, W=256, cam='synth', ds=0.5, bg=0.2, max_disp=1.0, scale=50),       # config 3 (B cut to 2)
+    dict(L=4, B=1, H=256, W=832, cam='kitti', ds=1, bg=1e-3, max_disp=0.4, scale=50),        # config 4, one view
+    dict(L=2, B=3, H=37, W=53, cam='synth', ds=1, bg=0.2, max_disp=1.0, scale=10),           # ragged sizes
+])
+def test_forward_splat_vs_oracle(lsi_mods, cfg):
+    from oracle import lsi_oracle as O
+    s = _scene(cfg['L'], cfg['B'], cfg['H'], cfg['W'], cfg['cam'], 0, cfg['max_disp'])
+    kw = dict(trg_downsampling=cfg['ds'], bg_layer_disp=cfg['bg'], max_disp=cfg['max_disp'], zbuf_scale=cfg['scale'])
+    cpu = [torch.tensor(s[k]).requires_grad_(True) for k in ('tex', 'mask', 'disp')]
+    cam_cpu = [torch.tensor(s[k]) for k in ('k_s', 'k_t', 'rot', 't')]
+    B, H, W = cfg['B'], cfg['H'], cfg['W']
+    for compose in (True, False):
+        ref = O.forward_splat(tuple(cpu), O.pixel_coords(B, H, W), *cam_cpu, compose_layers=compose,
+                              compute_trg_disp=True, **kw)
+        gpu = [torch.tensor(s[k], device='cuda').requires_grad_(True) for k in ('tex', 'mask', 'disp')]
+        out = lsi_mods['ldi'].forward_splat(tuple(gpu), lsi_mods['helpers'].pixel_coords(B, H, W),
+                                            *[x.cuda() for x in cam_cpu], compose_layers=compose,
+                                            compute_trg_disp=True, **kw)
+        for a, b, nme in zip(out, ref, ('img', 'wts', 'disp')):
+            assert_parity(a.detach().cpu(), b.detach(), tol=TOL, frac=1e-4, cap=2e-3, what='%s compose=%s' % (nme, compose))
+        gi = torch.randn(ref[0].shape, generator=torch.Generator().manual_seed(1))
+        g_ref = torch.autograd.grad((ref[0] * gi).sum(), cpu)
+        g_gpu = torch.autograd.grad((out[0] * gi.cuda()).sum(), gpu)
+        # fp32-vs-fp32 with a noisy reference: tex gradients to 1e-4, mask/disp gradients to 3e-4 (their own fp32
+        # noise floor is ~1e-4, see tests/test_oracle_golden.py::test_fp32_fixture_close_to_fp64_fixture); a
+        # threshold flip toggles d(omega)/dx for that pixel, so gradient outliers are bounded in number only
+        assert_parity(g_gpu[0].cpu(), g_ref[0], tol=TOL, frac=1e-4, what='dtex compose=%s' % compose)
+        assert_parity(g_gpu[1].cpu(), g_ref[1], tol=3 * TOL, frac=1e-4, what='dmask compose=%s' % compose)
+        assert_parity(g_gpu[2].cpu(), g_ref[2], tol=3 * TOL, frac=1e-4, what='ddisp compose=%s' % compose)
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes (no oracle: it would take minutes)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('L,B,H,W', [(4, 8, 256, 832), (5, 2, 512, 1664)])
+def test_full_size_properties(lsi_mods, L, B, H, W):
+    ldi, helpers = lsi_mods['ldi'], lsi_mods['helpers']
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    tex = torch.rand(L, B, H, W, 3, device='cuda', generator=gen)
+    mask = torch.ones(L, B, H, W, 1, device='cuda')
+    k = torch.tensor([[721.54 * W / 1242.0, 0, 609.56 * W / 1242.0], [0, 721.54 * H / 375.0, 172.85 * H / 375.0],
+                      [0, 0, 1.0]], device='cuda').expand(B, 3, 3).contiguous()
+    rot = torch.eye(3, device='cuda').expand(B, 3, 3).contiguous()
+    pc = helpers.pixel_coords(B, H, W)
+    kw = dict(bg_layer_disp=0.0, max_disp=0.4, zbuf_scale=50)
+    # (1) identity pose, one visible layer (others have d <= 0 => zero weight): render == texture, wts == w(d)
+    disp = torch.full((L, B, H, W, 1), -1.0, device='cuda')
+    disp[0] = 0.2
+    t0 = torch.zeros(B, 3, 1, device='cuda')
+    img, wts, dsp = ldi.forward_splat((tex, mask, disp), pc, k, k, rot, t0, compute_trg_disp=True, **kw)
+    assert (img[0] - tex[0]).abs().max().item() < 1e-6
+    assert (wts - 1.0).abs().max().item() < 1e-6                       # exp((0.5-0.5)*50) = 1
+    assert (dsp - 0.2).abs().max().item() < 1e-6
+    # (2) integer shift: fx*tx*d = n px exactly -> shifted copy, uncovered columns are 0/eps = 0 (bg 0)
+    n = 7
+    fx = 721.54 * W / 1242.0
+    tx = n / (fx * 0.2)
+    t1 = torch.tensor([[tx], [0.0], [0.0]], device='cuda').expand(B, 3, 1).contiguous()
+    img, wts = ldi.forward_splat((tex, mask, disp), pc, k, k, rot, t1, **kw)
+    assert (img[0, :, :, n + 1:-1] - tex[0, :, :, 1:-n - 1]).abs().max().item() < 2e-4   # sub-px residue of fp32 fx*tx*d
+    # (3) mass conservation: sum of weights == number of in-bounds source pixels (each splats total weight 1)
+    total = wts.double().sum().item()
+    assert abs(total - B * H * (W - n)) < 1e-3 * B * H * W
+    # (4) linearity of the un-normalised image in the texture: img*wts is linear in tex for fixed geometry
+    tex2 = torch.rand(L, B, H, W, 3, device='cuda', generator=gen)
+    disp_r = torch.rand(L, B, H, W, 1, device='cuda', generator=gen) * 0.4
+    a, wa = ldi.forward_splat((tex, mask, disp_r), pc, k, k, rot, t1, bg_layer_disp=1e-3, max_disp=0.4, zbuf_scale=10)
+    b, wb = ldi.forward_splat((tex2, mask, disp_r), pc, k, k, rot, t1, bg_layer_disp=1e-3, max_disp=0.4, zbuf_scale=10)
+    c, wc = ldi.forward_splat((0.25 * tex + 0.75 * tex2, mask, disp_r), pc, k, k, rot, t1, bg_layer_disp=1e-3,
+                              max_disp=0.4, zbuf_scale=10)
+    assert torch.equal(wa, wb) or (wa - wb).abs().max().item() < 1e-5 * wa.abs().max().item()
+    assert (c - (0.25 * a + 0.75 * b)).abs().max().item() < 1e-4
+    # (5) compose == sum of independent layers: img_c*wts_c == sum_l img_l*wts_l, wts_c == sum_l wts_l
+    il, wl = ldi.forward_splat((tex, mask, disp_r), pc, k, k, rot, t1, compose_layers=False, bg_layer_disp=1e-3,
+                               max_disp=0.4, zbuf_scale=10)
+    assert rel_err(wa.cpu(), wl.sum(0, keepdim=True).cpu()) < 1e-5
+    assert rel_err((a * wa).cpu(), (il * wl).sum(0, keepdim=True).cpu()) < 1e-5
+
+
+def test_host_entry_point_matches_device_path(lsi_mods):
+    """lsi_b200_forward_splat_host (host buffers in, host buffers out) == the device-pointer path."""
+    b200, ldi, helpers = lsi_mods['b200'], lsi_mods['ldi'], lsi_mods['helpers']
+    g = load_golden('fs_kitti_ds05')
+    c, kw = _cuda_case(g)
+    L, B, H, W, _ = g['in_tex'].shape
+    ht, wt = H // 2, W // 2
+    ref = ldi.forward_splat((c('tex'), c('mask'), c('disp')), helpers.pixel_coords(B, H, W), c('k_s'), c('k_t'),
+                            c('rot'), c('t'), compute_trg_disp=True, **kw)
+    desc = b200.SplatDesc(L, B, H, W, ht, wt, 0.5, float(g['in_bg']), float(g['in_max_disp']), float(g['in_scale']),
+                          1, 1, 3, 1, 1, 0)
+    arrs = {k: np.ascontiguousarray(g['in_' + k], dtype=np.float32) for k in ('tex', 'mask', 'disp', 'k_s', 'k_t', 'rot', 't')}
+    img = np.empty((1, B, ht, wt, 3), np.float32)
+    wts = np.empty((1, B, ht, wt, 1), np.float32)
+    dsp = np.empty((1, B, ht, wt, 1), np.float32)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    b200.call('lsi_b200_forward_splat_host', desc, p(arrs['tex']), p(arrs['mask']), p(arrs['disp']), p(arrs['k_s']),
+              p(arrs['k_t']), p(arrs['rot']), p(arrs['t']), p(img), p(wts), p(dsp))
+    for a, b in zip((img, wts, dsp), ref):
+        assert rel_err(a, b.cpu()) < 1e-6
+
+
+def test_error_behaviour(lsi_mods):
+    ldi, helpers, b200 = lsi_mods['ldi'], lsi_mods['helpers'], lsi_mods['b200']
+    tex = torch.rand(1, 1, 8, 8, 3, device='cuda')
+    disp = torch.rand(1, 1, 8, 8, 1, device='cuda')
+    k = torch.eye(3, device='cuda')[None]
+    t = torch.zeros(1, 3, 1, device='cuda')
+    pc = helpers.pixel_coords(1, 8, 8)
+    with pytest.raises(RuntimeError):
+        ldi.forward_splat((tex.cpu(), None, disp), pc, k, k, k, t)                 # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        ldi.forward_splat((tex.double(), None, disp), pc, k, k, k, t)              # wrong dtype
+    with pytest.raises(RuntimeError):
+        ldi.forward_splat((tex, None, disp[:, :, :4]), pc, k, k, k, t)             # shape mismatch
+    with pytest.raises(RuntimeError):
+        ldi.forward_splat((tex, None, disp), pc, k, k, k, t, trg_downsampling=0.3)  # non-integral target size
+    desc = b200.SplatDesc(1, 1, 8, 8, 8, 8, 1.0, 0.0, 0.0, 10.0, 1, 0, 3, 1, 1, 0)   # max_disp == 0
+    assert b200.lib().lsi_b200_forward_splat_workspace_bytes(desc) == 0
+    assert b'max_disp' in b200.lib().lsi_b200_last_error()
