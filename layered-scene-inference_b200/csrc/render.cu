@@ -10,6 +10,7 @@
 
 #include "capi_common.h"
 #include "common.cuh"
+#include "render_fast.cuh"
 
 namespace lsi {
 
@@ -451,6 +452,13 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   if (has_disp && layer_acc)
     LSI_CUDA(cudaMemsetAsync(layer_acc, 0, (size_t)d->n_layers * d->batch * n_trg * 8, st));
 
+  const bool bc_fits_grid = pl.bc <= 65535;
+  // fast path: standard grid, no focal shift, no trg_disp, 16-byte aligned rows, planar (3/1/1) or packed (4/4) layout
+  const bool packed = d->tex_px_stride == 4 && d->disp_px_stride == 4 && disp == tex + 3;
+  const bool planar = d->tex_px_stride == 3 && d->disp_px_stride == 1;
+  const bool fast = (d->variant == 0 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
+                    (!mask || d->mask_px_stride == 1) && (!packed || ((uintptr_t)tex & 15) == 0) && d->h_s <= 65535 &&
+                    bc_fits_grid;
   for (int b0 = 0; b0 < d->batch; b0 += pl.bc) {
     const int bc = (d->batch - b0 < pl.bc) ? d->batch - b0 : pl.bc;
     FwdParams p;
@@ -465,6 +473,38 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
     p.gp = geom_of(d);
     LSI_CUDA(cudaMemsetAsync(p.acc4, 0, (size_t)pl.nl_acc * bc * n_trg * 16, st));
     if (own_accd) LSI_CUDA(cudaMemsetAsync(p.accd, 0, (size_t)d->n_layers * bc * n_trg * 8, st));
+    if (fast) {
+      FastParams f;
+      f.tex = tex; f.disp = disp; f.mask = mask; f.mats = mats; f.acc4 = p.acc4;
+      f.L = d->n_layers; f.B = d->batch; f.H = d->h_s; f.W = d->w_s; f.b0 = b0; f.bc = bc;
+      f.acc_per_layer = p.acc_per_layer; f.w_t = d->w_t; f.h_t = d->h_t;
+      f.ds = d->trg_downsampling; f.inv_max_disp = 1.f / d->max_disp;
+      f.k2 = d->zbuf_scale * 1.4426950408889634f; f.k2h = 0.5f * f.k2;
+      f.ablate = (d->variant >= 100) ? d->variant - 100 : 0;
+      dim3 fgrid((d->w_s + 63) / 64, d->h_s, bc), fblock(64);
+      {
+        ScopedTiming tm(kSplatFwd, st);
+        if (packed) {
+          if (mask) launch3(splat_fwd_fast_kernel<true, true>, fgrid, fblock, st, f);
+          else launch3(splat_fwd_fast_kernel<false, true>, fgrid, fblock, st, f);
+        } else {
+          if (mask) launch3(splat_fwd_fast_kernel<true, false>, fgrid, fblock, st, f);
+          else launch3(splat_fwd_fast_kernel<false, false>, fgrid, fblock, st, f);
+        }
+      }
+      LSI_LAUNCH_CHECK();
+      if (n_trg % 4 == 0 && ((uintptr_t)trg_img & 15) == 0 && ((uintptr_t)trg_wts & 15) == 0) {
+        NormFastParams nf;
+        nf.acc4 = p.acc4; nf.img = trg_img; nf.wts = trg_wts; nf.B = d->batch; nf.b0 = b0; nf.bc = bc; nf.n_trg = n_trg;
+        nf.nb = d->compose_layers ? (float)d->n_layers * bg_weight(d) : bg_weight(d);
+        {
+          ScopedTiming tm(kNormalize, st);
+          normalize_fast_kernel<<<dim3((n_trg / 4 + 255) / 256, bc, pl.nl_acc), 256, 0, st>>>(nf);
+        }
+        LSI_LAUNCH_CHECK();
+        continue;
+      }
+    } else {
     dim3 grid((n_src + 255) / 256, d->n_layers, bc), block(256);
     const int sel = (mask ? 4 : 0) | (pixel_coords ? 2 : 0) | (has_disp ? 1 : 0);
     {
@@ -481,6 +521,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
     }
     }
     LSI_LAUNCH_CHECK();
+    }
     NormParams np;
     np.acc4 = p.acc4; np.accd = p.accd; np.img = trg_img; np.wts = trg_wts; np.disp = has_disp ? trg_disp : nullptr;
     np.L = d->n_layers; np.B = d->batch; np.b0 = b0; np.bc = bc; np.n_trg = n_trg; np.compose = d->compose_layers ? 1 : 0;

@@ -39,6 +39,7 @@ def assert_parity(a, b, tol=1e-4, frac=1e-4, cap=None, what=''):
     evaluations differ like that (6 of 106,496 px > 5e-5 on the 128x416 config), so: all but `frac` of the elements
     within `tol` (relative to the tensor's max), and -- for forward values -- nothing beyond `cap`."""
     f, m = outlier_frac(a, b, tol)
-    assert f <= frac, '%s: %.3g of elements beyond %g (max %.3g)' % (what, f, tol, m)
+    n = np.asarray(b).size
+    assert f * n <= max(frac * n, 8.0), '%s: %.3g of %d elements beyond %g (max %.3g)' % (what, f, n, tol, m)
     if cap is not None:
         assert m <= cap, '%s: max error %.3g beyond cap %g' % (what, m, cap)
