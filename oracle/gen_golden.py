@@ -304,8 +304,68 @@ def gen_loss():
         print('%-28s %7.1f KB' % (name, os.path.getsize(path) / 1024.0))
 
 
+# ---------------------------------------------------------------------------------------------------
+# the CNN: the reference's own lsi/nnutils/nets.py wiring over the slim stand-in
+# ---------------------------------------------------------------------------------------------------
+def gen_nets():
+    from lsi.nnutils import nets
+    sys.path.insert(0, ROOT)
+    from oracle import lsi_oracle_nets as N
+    L, B, H, W, steps, max_disp = 2, 2, 128, 128, 3, 1.0
+    rs = np.random.RandomState(41)
+    img = rs.uniform(0, 1, (B, H, W, 3)).astype(np.float32)
+    g_pred = np.random.RandomState(42).normal(0, 1, (L, B, H, W, 4)).astype(np.float32)   # regenerated by the tests
+    blob = dict(in_img=img, meta=np.array([L, B, H, W, steps], dtype=np.int64), max_disp=np.float64(max_disp),
+                param_seed=np.int64(7), g_seed=np.int64(42))
+    for dtype, sfx in ((torch.float32, '_f32'), (torch.float64, '_f64')):
+        tf._set_float(dtype)
+        params = N.init_params(L, seed=7, n_layerwise_steps=steps, random_beta=True, dtype=dtype)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        tf._VARS.clear()
+        tf._VARS.update(leaves)
+        x = torch.tensor(img, dtype=dtype, requires_grad=True)
+        _, feat_dec, skip_feat, _ = nets.encoder_decoder_unet(T(x), nl_diff_enc_dec=steps)       # ldi_enc_dec.py:196-199
+        ldi_pred = nets.ldi_predictor(feat_dec, n_layers=L, n_layerwise_steps=steps, skip_feat=skip_feat)
+        tex, masks, disps = (v.t for v in ldi_pred)
+        disps = disps * max_disp                                                                  # ldi_enc_dec.py:213
+        pred = torch.cat([tex, disps], dim=-1)
+        assert float(masks.min()) == 1.0 and float(masks.max()) == 1.0
+        # fixtures stay small: strided samples of the big tensors plus fp64 checksums of the whole tensors
+        blob['pred' + sfx] = pred.detach()[:, :, ::4, ::4, :].numpy().astype(np.float32)
+        blob['feat_dec' + sfx] = feat_dec.t.detach()[:, ::2, ::2, ::4].numpy().astype(np.float32)
+        blob['pred_stats' + sfx] = np.array([float(pred.double().sum()), float(pred.double().pow(2).sum().sqrt())])
+        s = (pred * torch.tensor(g_pred, dtype=dtype)).sum()
+        names = sorted(leaves)
+        grads = torch.autograd.grad(s, [leaves[n] for n in names] + [x])
+        blob['d_img' + sfx] = grads[-1][:, ::4, ::4].numpy().astype(np.float32)
+        blob['d_img_stats' + sfx] = np.array([float(grads[-1].double().sum()), float(grads[-1].double().pow(2).sum().sqrt())])
+        keep = ['encoder_decoder_unet/cnv1/weights', 'encoder_decoder_unet/cnv1/BatchNorm/beta',
+                'encoder_decoder_unet/cnv7b/BatchNorm/beta', 'encoder_decoder_unet/icnv4/BatchNorm/beta',
+                'ldi_tex_disp/pixelwise_pred/upsample_1/pred_1/weights', 'ldi_tex_disp/pixelwise_pred/upsample_1/pred_1/biases',
+                'ldi_tex_disp/pixelwise_pred/upsample_0/decoder/upcnv1/weights',
+                'ldi_tex_disp/pixelwise_pred/upsample_0/decoder/upcnv3b/BatchNorm/beta']
+        for n, g in zip(names, grads[:-1]):
+            if n in keep:
+                blob['grad:' + n + sfx] = g.numpy().astype(np.float32)
+        blob['grad_names'] = np.array(names)
+        blob['grad_sum' + sfx] = np.array([float(g.double().sum()) for g in grads[:-1]])
+        blob['grad_l2' + sfx] = np.array([float(g.double().pow(2).sum().sqrt()) for g in grads[:-1]])
+        extra = [k for k in tf._VARS if k not in leaves]
+        assert all(('/fc/' in k) or any(t in k for t in ('icnv3', 'icnv2', 'icnv1', 'unet/upcnv3', 'unet/upcnv2', 'unet/upcnv1'))
+                   for k in extra), extra          # only the never-executed parts may be missing from the oracle's list
+    path = os.path.join(GOLD, 'nets_unet_l2.npz')
+    np.savez_compressed(path, **blob)
+    print('%-28s %7.1f KB' % ('nets_unet_l2', os.path.getsize(path) / 1024.0))
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    gen_forward_splat()
-    gen_primitives()
-    gen_loss()
+    which = sys.argv[1:] or ['fs', 'prim', 'loss', 'nets']
+    if 'fs' in which:
+        gen_forward_splat()
+    if 'prim' in which:
+        gen_primitives()
+    if 'loss' in which:
+        gen_loss()
+    if 'nets' in which:
+        gen_nets()

@@ -402,3 +402,38 @@ image = _Obj(resize_images=lambda images, size, method=None: _resize_area(images
 summary = _Obj(scalar=lambda *a, **k: None, image=lambda *a, **k: None,
                histogram=lambda *a, **k: None)
 train = _Obj()
+
+
+# ---------------------------------------------------------------------------------------------------
+# variable scopes + a flat variable store (used by the slim stand-in for lsi/nnutils/nets.py)
+# ---------------------------------------------------------------------------------------------------
+_VARS = {}
+_SCOPES = []
+
+
+class _Scope(object):
+    def __init__(self, name):
+        self.name = name
+        self.original_name_scope = name + '/'
+
+
+@contextlib.contextmanager
+def variable_scope(name, reuse=None):
+    _SCOPES.append(name if name is not None else 'default')
+    try:
+        yield _Scope('/'.join(_SCOPES))
+    finally:
+        _SCOPES.pop()
+
+
+def current_scope():
+    return '/'.join(_SCOPES)
+
+
+def get_variable(name, shape, init):
+    full = current_scope() + '/' + name
+    if full not in _VARS:
+        _VARS[full] = init(list(shape))
+    v = _VARS[full]
+    assert list(v.shape) == list(shape), (full, list(v.shape), list(shape))
+    return v
