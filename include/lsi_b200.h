@@ -159,6 +159,56 @@ LSI_B200_API int lsi_b200_decreasing_disp_loss(const float* disp, int n_layers, 
 LSI_B200_API int lsi_b200_decreasing_disp_loss_backward(const float* disp, int n_layers, long long n_pixels,
                                            const float* g_loss, float* d_disp, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * CNN slice: lsi/nnutils/nets.py (slim.conv2d / conv2d_transpose / batch_norm), train_utils.py:107-117 (Adam).
+ * fp32 NHWC; weights in TF layouts ([kh,kw,cin,cout] conv, [kh,kw,cout,cin] transposed conv) addressed by strides.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lsi_b200_conv_desc {
+  int batch, h_in, w_in, c_in, h_out, w_out, c_out;
+  int kh, kw, stride, pad_top, pad_left;        /* TF SAME: pad_before = total/2 (asymmetric at stride 2)            */
+  int mode;                                     /* 0: out(oy) gathers in(oy*stride - pad + ky)   (conv fwd, convT dgrad) */
+                                                /* 1: out(oy) gathers in((oy + pad - ky)/stride) (convT fwd, conv dgrad) */
+  int w_tap_stride, w_ci_stride, w_co_stride;   /* element strides of the weights for (tap, summed ch, produced ch)  */
+  int in_c_stride, out_c_stride;                /* pixel strides (>= channels): channel slices of concat buffers      */
+  int epilogue;                                 /* 0 none; 1 + bias; 2 sigmoid(. + bias) (nets.py:143,154-155)        */
+  int accumulate;                               /* out += result (gradient accumulation into shared skip tensors)    */
+} lsi_b200_conv_desc;
+
+/* slim.conv2d (nets.py:273-286,...) / slim.conv2d_transpose (nets.py:296,...) forward and both data gradients. */
+LSI_B200_API int lsi_b200_conv2d(const lsi_b200_conv_desc* d, const float* in, const float* w, const float* bias,
+                                 float* out, void* stream);
+/* Weight gradient: dw[tap][a][b] = sum big(oy*stride - pad + ky)[a] * small(oy)[b]; `big` is described by the
+ * descriptor's *_in fields, `small` by its *_out fields (conv: big = input, small = dout; convT: big = dout,
+ * small = input -- which yields the TF layout of either op directly). */
+LSI_B200_API int lsi_b200_conv2d_wgrad(const lsi_b200_conv_desc* d, const float* big, const float* small, float* dw,
+                                       void* stream);
+
+/* slim.batch_norm(is_training=True, center=True, scale=False) + ReLU (nets.py:263-272): batch statistics over the
+ * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward.  workspace:
+ * lsi_b200_bn_workspace_bytes(channels). */
+LSI_B200_API size_t lsi_b200_bn_workspace_bytes(int channels);
+LSI_B200_API int lsi_b200_bn_relu_forward(const float* x, const float* beta, float* y, float* stats, long long n_pixels,
+                                          int channels, int x_c_stride, int y_c_stride, float eps, int relu,
+                                          void* workspace, void* stream);
+/* dx (and dbeta_sums[c] = (sum dz, sum dz*xhat); dbeta = the first) from dy, with dz = dy*[y>0] when relu. */
+LSI_B200_API int lsi_b200_bn_relu_backward(const float* x, const float* y, const float* dy, const float* stats, float* dx,
+                                           float* dbeta_sums, long long n_pixels, int channels, int x_c_stride,
+                                           int y_c_stride, int dy_c_stride, int dx_c_stride, int relu, int accumulate,
+                                           void* workspace, void* stream);
+/* sums[c] = (sum_x, sum_x^2) over pixels (bias gradients of the prediction conv). */
+LSI_B200_API int lsi_b200_channel_sums(const float* x, float* sums, long long n_pixels, int channels, int x_c_stride,
+                                       void* workspace, void* stream);
+/* dst[q][0..C) (+)= src[q][0..C) with independent pixel strides: tf.concat (nets.py:300,...) and its gradient. */
+LSI_B200_API int lsi_b200_copy_channels(const float* src, float* dst, long long n_pixels, int channels, int src_c_stride,
+                                        int dst_c_stride, int accumulate, void* stream);
+/* dz = dy * y * (1 - y) for the sigmoid prediction head. */
+LSI_B200_API int lsi_b200_sigmoid_backward(const float* y, const float* dy, float* dz, long long n, void* stream);
+/* tf.train.AdamOptimizer.apply_gradients (train_utils.py:112-115) on one flat parameter buffer; grads are scaled by
+ * grad_scale first (1/world_size after the all-reduce). step counts from 1. */
+LSI_B200_API int lsi_b200_adam_step(float* params, const float* grads, float* m, float* v, long long n, float learning_rate,
+                                    float beta1, float beta2, float epsilon, long long step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,258 @@
+// Normalisation / activation / optimiser kernels of the CNN slice (fp32, NHWC, channel-last so that a warp reads
+// consecutive channels of consecutive pixels).
+//   batch-stat BN + ReLU  slim.batch_norm(center=True, scale=False, eps=1e-3, is_training=True) (nets.py:263-272):
+//                          y = relu((x - mean_B) * rsqrt(var_B + eps) + beta), biased variance over (N,H,W)
+//   sigmoid head           pixelwise_predictor's activation (nets.py:143); forward is fused into the conv epilogue
+//   Adam                   tf.train.AdamOptimizer(lr, beta1) (train_utils.py:112): m,v update with the
+//                          lr*sqrt(1-b2^t)/(1-b1^t) step and epsilon outside the square root
+#include "capi_common.h"
+#include "common.cuh"
+
+namespace lsi {
+
+constexpr int kStatBlocks = 512;
+
+// partial[blk][c] = (sum_a, sum_b) over the block's pixel range; a/b chosen by mode:
+//   mode 0 (forward stats):   a = x,            b = x*x
+//   mode 1 (backward stats):  a = dz,           b = dz * xhat    with dz = dy * [y > 0], xhat = (x - mean) * invstd
+struct StatParams {
+  const float* x; const float* y; const float* dy; const float* stats;   // stats [C][2] = (mean, invstd)
+  double* partial;                                                          // [kStatBlocks][C][2]
+  long long P; int C, x_cs, y_cs, dy_cs, mode, relu;
+};
+
+__global__ void __launch_bounds__(256) channel_stats_kernel(const StatParams p) {
+  // thread -> (pixel lane, channel): channels fastest so that loads coalesce
+  const int lanes = 256 / min(p.C, 256) > 0 ? 256 / min(p.C, 256) : 1;
+  const int cpt = (p.C + 255) / 256;                 // channels per thread when C > 256
+  const int c_lo = (p.C >= 256) ? threadIdx.x : (int)threadIdx.x % p.C;
+  const int lane = (p.C >= 256) ? 0 : (int)threadIdx.x / p.C;
+  const bool active = (p.C >= 256) || lane < lanes;
+  const long long per_blk = (p.P + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per_blk, p1 = (p0 + per_blk < p.P) ? p0 + per_blk : p.P;
+  for (int k = 0; k < cpt; ++k) {
+    const int c = c_lo + k * 256;
+    double sa = 0.0, sb = 0.0;
+    if (active && c < p.C) {
+      float mean = 0.f, invstd = 0.f;
+      if (p.mode == 1) { mean = p.stats[2 * c]; invstd = p.stats[2 * c + 1]; }
+      float fa = 0.f, fb = 0.f; int cnt = 0;
+      for (long long q = p0 + lane; q < p1; q += lanes) {
+        const float xv = p.x[q * p.x_cs + c];
+        if (p.mode == 0) { fa += xv; fb = fmaf(xv, xv, fb); }
+        else {
+          float dz = p.dy[q * p.dy_cs + c];
+          if (p.relu && !(p.y[q * p.y_cs + c] > 0.f)) dz = 0.f;
+          fa += dz; fb = fmaf(dz, (xv - mean) * invstd, fb);
+        }
+        if (++cnt == 256) { sa += fa; sb += fb; fa = fb = 0.f; cnt = 0; }   // fp32 runs of 256, fp64 across runs
+      }
+      sa += fa; sb += fb;
+    }
+    // combine the pixel lanes that share a channel (C < 256): shared-memory tree over lanes
+    __shared__ double sh[2][256];
+    sh[0][threadIdx.x] = sa; sh[1][threadIdx.x] = sb;
+    __syncthreads();
+    if (p.C < 256) {
+      if (lane == 0 && c < p.C) {
+        for (int l = 1; l < lanes; ++l) { sa += sh[0][l * p.C + c]; sb += sh[1][l * p.C + c]; }
+      }
+    }
+    if (lane == 0 && c < p.C && active) {
+      p.partial[((size_t)blockIdx.x * p.C + c) * 2] = sa;
+      p.partial[((size_t)blockIdx.x * p.C + c) * 2 + 1] = sb;
+    }
+    __syncthreads();
+  }
+}
+
+// forward: stats[c] = (mean, rsqrt(var + eps)); backward: stats_out[c] = (sum dz, sum dz*xhat)
+__global__ void finalize_stats_kernel(const double* __restrict__ partial, int nblk, int C, long long P, float eps, int mode,
+                                      float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblk; ++i) { a += partial[((size_t)i * C + c) * 2]; b += partial[((size_t)i * C + c) * 2 + 1]; }
+  if (mode == 0) {
+    const double mean = a / (double)P;
+    double var = b / (double)P - mean * mean;
+    if (var < 0.0) var = 0.0;
+    out[2 * c] = (float)mean; out[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  } else {
+    out[2 * c] = (float)a; out[2 * c + 1] = (float)b;
+  }
+}
+
+struct BnApplyParams {
+  const float* x; const float* stats; const float* beta; float* y;
+  long long P; int C, x_cs, y_cs, relu;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
+  const long long total = p.P * p.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / p.C; const int c = (int)(i - q * p.C);
+    float v = (p.x[q * p.x_cs + c] - __ldg(p.stats + 2 * c)) * __ldg(p.stats + 2 * c + 1) + __ldg(p.beta + c);
+    if (p.relu) v = fmaxf(v, 0.f);
+    p.y[q * p.y_cs + c] = v;
+  }
+}
+
+// dx = invstd * (dz - mean(dz) - xhat * mean(dz * xhat)),  dz = dy * [y > 0];  dbeta = sum dz (from the stats pass)
+struct BnBwdParams {
+  const float* x; const float* y; const float* dy; const float* stats; const float* sums; float* dx;
+  long long P; int C, x_cs, y_cs, dy_cs, dx_cs, relu, accumulate;
+};
+
+__global__ void __launch_bounds__(256) bn_backward_kernel(const BnBwdParams p) {
+  const long long total = p.P * p.C;
+  const float invP = 1.f / (float)p.P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / p.C; const int c = (int)(i - q * p.C);
+    const float mean = __ldg(p.stats + 2 * c), invstd = __ldg(p.stats + 2 * c + 1);
+    float dz = p.dy[q * p.dy_cs + c];
+    if (p.relu && !(p.y[q * p.y_cs + c] > 0.f)) dz = 0.f;
+    const float xhat = (p.x[q * p.x_cs + c] - mean) * invstd;
+    float v = invstd * (dz - __ldg(p.sums + 2 * c) * invP - xhat * __ldg(p.sums + 2 * c + 1) * invP);
+    if (p.accumulate) v += p.dx[q * p.dx_cs + c];
+    p.dx[q * p.dx_cs + c] = v;
+  }
+}
+
+// dst[q][0..C) (+)= src[q][0..C)   with independent pixel strides (concat / gradient split without torch ops)
+__global__ void __launch_bounds__(256) copy_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, long long P,
+                                                            int C, int src_cs, int dst_cs, int accumulate) {
+  const long long total = P * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / C; const int c = (int)(i - q * C);
+    const float v = src[q * src_cs + c];
+    if (accumulate) dst[q * dst_cs + c] += v; else dst[q * dst_cs + c] = v;
+  }
+}
+
+// sigmoid head backward: dz = dy * y * (1 - y)  (y = sigmoid output), written in place of a fresh buffer
+__global__ void __launch_bounds__(256) sigmoid_backward_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                               float* __restrict__ dz, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    dz[i] = dy[i] * v * (1.f - v);
+  }
+}
+
+struct AdamParams {
+  float* p; const float* g; float* m; float* v;
+  long long n; float lr_t, beta1, beta2, eps, grad_scale;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamParams a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = a.g[i] * a.grad_scale;
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.m[i] = m; a.v[i] = v;
+    a.p[i] -= a.lr_t * m / (sqrtf(v) + a.eps);
+  }
+}
+
+static unsigned ew_grid(long long n) {
+  long long g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace lsi
+
+using namespace lsi;
+
+extern "C" size_t lsi_b200_bn_workspace_bytes(int channels) {
+  return (size_t)kStatBlocks * (size_t)(channels > 0 ? channels : 1) * 2 * sizeof(double);
+}
+
+static int stat_blocks(long long P) {
+  long long b = (P + 63) / 64;
+  if (b > kStatBlocks) b = kStatBlocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int lsi_b200_bn_relu_forward(const float* x, const float* beta, float* y, float* stats, long long n_pixels,
+                                        int channels, int x_c_stride, int y_c_stride, float eps, int relu, void* workspace,
+                                        void* stream) {
+  LSI_REQUIRE(x && beta && y && stats && workspace, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 1 && x_c_stride >= channels && y_c_stride >= channels, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  const int nb = stat_blocks(n_pixels);
+  StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
+  channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
+  LSI_LAUNCH_CHECK();
+  finalize_stats_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, eps, 0, stats);
+  LSI_LAUNCH_CHECK();
+  BnApplyParams ap{x, stats, beta, y, n_pixels, channels, x_c_stride, y_c_stride, relu};
+  bn_apply_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(ap);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_bn_relu_backward(const float* x, const float* y, const float* dy, const float* stats, float* dx,
+                                         float* dbeta_sums, long long n_pixels, int channels, int x_c_stride, int y_c_stride,
+                                         int dy_c_stride, int dx_c_stride, int relu, int accumulate, void* workspace,
+                                         void* stream) {
+  LSI_REQUIRE(x && y && dy && stats && dx && dbeta_sums && workspace, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 1, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  const int nb = stat_blocks(n_pixels);
+  StatParams sp{x, y, dy, stats, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, 1, relu};
+  channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
+  LSI_LAUNCH_CHECK();
+  finalize_stats_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, dbeta_sums);
+  LSI_LAUNCH_CHECK();
+  BnBwdParams bp{x, y, dy, stats, dbeta_sums, dx, n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, dx_c_stride, relu, accumulate};
+  bn_backward_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(bp);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_channel_sums(const float* x, float* sums, long long n_pixels, int channels, int x_c_stride,
+                                     void* workspace, void* stream) {
+  // sums[c][0] = sum over pixels of x[., c] (bias gradients); sums[c][1] = sum of squares
+  LSI_REQUIRE(x && sums && workspace, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 1 && x_c_stride >= channels, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  const int nb = stat_blocks(n_pixels);
+  StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
+  channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
+  LSI_LAUNCH_CHECK();
+  finalize_stats_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, sums);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_copy_channels(const float* src, float* dst, long long n_pixels, int channels, int src_c_stride,
+                                      int dst_c_stride, int accumulate, void* stream) {
+  LSI_REQUIRE(src && dst, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 1 && src_c_stride >= channels && dst_c_stride >= channels, "bad sizes");
+  copy_channels_kernel<<<ew_grid(n_pixels * channels), 256, 0, as_stream(stream)>>>(src, dst, n_pixels, channels, src_c_stride,
+                                                                                     dst_c_stride, accumulate);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_sigmoid_backward(const float* y, const float* dy, float* dz, long long n, void* stream) {
+  LSI_REQUIRE(y && dy && dz && n >= 1, "bad arguments");
+  sigmoid_backward_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, dy, dz, n);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_adam_step(float* params, const float* grads, float* m, float* v, long long n, float learning_rate,
+                                  float beta1, float beta2, float epsilon, long long step, float grad_scale, void* stream) {
+  LSI_REQUIRE(params && grads && m && v && n >= 1 && step >= 1, "bad arguments");
+  AdamParams a;
+  a.p = params; a.g = grads; a.m = m; a.v = v; a.n = n;
+  a.lr_t = (float)((double)learning_rate * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = epsilon; a.grad_scale = grad_scale;
+  adam_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(a);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}

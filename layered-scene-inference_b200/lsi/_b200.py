@@ -21,9 +21,18 @@ class SplatDesc(ctypes.Structure):
                 ('variant', ctypes.c_int)]
 
 
+class ConvDesc(ctypes.Structure):
+    """struct lsi_b200_conv_desc (include/lsi_b200.h)."""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ('batch', 'h_in', 'w_in', 'c_in', 'h_out', 'w_out', 'c_out', 'kh', 'kw', 'stride', 'pad_top', 'pad_left',
+                 'mode', 'w_tap_stride', 'w_ci_stride', 'w_co_stride', 'in_c_stride', 'out_c_stride', 'epilogue',
+                 'accumulate')]
+
+
 # name -> (restype, argtypes); mirrors include/lsi_b200.h one to one (tests/test_capi_symbols.py checks)
 _P, _I, _F, _LL, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t
 _DP = ctypes.POINTER(SplatDesc)
+_CP = ctypes.POINTER(ConvDesc)
 SIGNATURES = {
     'lsi_b200_version': (_I, []),
     'lsi_b200_last_error': (ctypes.c_char_p, []),
@@ -49,6 +58,15 @@ SIGNATURES = {
     'lsi_b200_disp_smoothness_loss_backward': (_I, [_P, _I, _I, _I, _P, _P, _P]),
     'lsi_b200_decreasing_disp_loss': (_I, [_P, _I, _LL, _P, _P, _P]),
     'lsi_b200_decreasing_disp_loss_backward': (_I, [_P, _I, _LL, _P, _P, _P]),
+    'lsi_b200_conv2d': (_I, [_CP, _P, _P, _P, _P, _P]),
+    'lsi_b200_conv2d_wgrad': (_I, [_CP, _P, _P, _P, _P]),
+    'lsi_b200_bn_workspace_bytes': (_SZ, [_I]),
+    'lsi_b200_bn_relu_forward': (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _F, _I, _P, _P]),
+    'lsi_b200_bn_relu_backward': (_I, [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'lsi_b200_channel_sums': (_I, [_P, _P, _LL, _I, _I, _P, _P]),
+    'lsi_b200_copy_channels': (_I, [_P, _P, _LL, _I, _I, _I, _I, _P]),
+    'lsi_b200_sigmoid_backward': (_I, [_P, _P, _P, _LL, _P]),
+    'lsi_b200_adam_step': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _LL, _F, _P]),
 }
 
 

@@ -1,0 +1,404 @@
+"""Mirror of lsi/nnutils/nets.py (reference tree): the encoder-decoder U-Net and the per-layer LDI prediction heads.
+
+Same function names, arguments and return values as the reference; the layers run as CUDA kernels behind the C ABI
+(lsi_b200_conv2d / _conv2d_wgrad / _bn_relu_forward / _bn_relu_backward / ... in include/lsi_b200.h).  Semantics
+follow TF-1.4 slim as the reference uses it: NHWC, SAME padding (asymmetric at stride 2), conv -> batch-stat BN (beta
+only, eps 1e-3, biased variance) -> ReLU with no conv bias; the prediction conv has bias + sigmoid and no BN; 4x4
+stride-2 transposed conv.  Variables are named exactly as TF names them (`encoder_decoder_unet/cnv1/weights`,
+`.../BatchNorm/beta`, `ldi_tex_disp/pixelwise_pred/upsample_<l>/decoder/upcnv3/weights`, `.../pred_<l>/biases`), kept in
+a `ParamStore` that plays the role of the TF variable scope (`reuse=True` looks variables up instead of creating them).
+
+Not provided (never executed by either reference script): the FC stack on the bottleneck (nets.py:289-291, its output
+`feat` is discarded at ldi_enc_dec.py:198 -- `None` is returned in its place), the decoder levels below the one that
+feeds the heads, `encoder_simple`/`encoder_decoder_simple` (`--use_unet=false`, unused by every documented recipe), and
+inference-mode batch norm (the reference never updates the moving averages, train_utils.py:107-117, and evaluates with
+batch statistics, ldi_pred_eval.py:45).
+"""
+import math
+import zlib
+
+import numpy as np
+import torch
+
+from lsi import _b200
+from lsi.nnutils import helpers as nn_helpers
+
+BN_EPS = 1e-3     # [TF1.4] slim.batch_norm default epsilon
+
+ENC = [('cnv1', 7, 2, 32), ('cnv1b', 7, 1, 32), ('cnv2', 5, 2, 64), ('cnv2b', 5, 1, 64), ('cnv3', 3, 2, 128),
+       ('cnv3b', 3, 1, 128), ('cnv4', 3, 2, 256), ('cnv4b', 3, 1, 256), ('cnv5', 3, 2, 512), ('cnv5b', 3, 1, 512),
+       ('cnv6', 3, 2, 512), ('cnv6b', 3, 1, 512), ('cnv7', 3, 2, 512), ('cnv7b', 3, 1, 512)]          # nets.py:273-286
+DEC = [(7, 512, 'cnv6b'), (6, 512, 'cnv5b'), (5, 256, 'cnv4b'), (4, 128, 'cnv3b'), (3, 64, 'cnv2b'), (2, 32, 'cnv1b'),
+       (1, 32, None)]                                                                                   # nets.py:296-345
+HEAD_FILTERS = [32, 64, 128, 256]                                                                       # nets.py:87
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# variables
+# ---------------------------------------------------------------------------------------------------------------------
+class ParamStore(object):
+    """TF-variable-scope stand-in: name -> leaf tensor.  `flatten()` re-packs every variable (and its gradient) into
+    one contiguous buffer each, which is what the NCCL all-reduce and the fused Adam kernel operate on."""
+
+    def __init__(self, device='cuda', seed=0):
+        self.device = torch.device(device)
+        self.seed = seed
+        self.vars = {}
+        self.flat = None
+        self.flat_grad = None
+
+    def get(self, name, shape, reuse, kind):
+        if name in self.vars:
+            v = self.vars[name]
+            if list(v.shape) != list(shape):
+                raise RuntimeError('variable %s has shape %s, requested %s' % (name, list(v.shape), list(shape)))
+            return v
+        if reuse:
+            raise RuntimeError('variable %s does not exist (reuse=True)' % name)
+        if self.flat is not None:
+            raise RuntimeError('ParamStore is already flattened; create every variable first')
+        rs = np.random.RandomState((zlib.crc32(name.encode()) + self.seed) % (2 ** 31))
+        if kind == 'weights':          # [TF1.4] slim default: Xavier-uniform
+            kh, kw, a, b = shape
+            limit = math.sqrt(6.0 / (kh * kw * a + kh * kw * b))
+            v = torch.tensor(rs.uniform(-limit, limit, shape), dtype=torch.float32)
+        else:                          # biases / BatchNorm beta: zeros
+            v = torch.zeros(shape, dtype=torch.float32)
+        v = v.to(self.device).requires_grad_(True)
+        self.vars[name] = v
+        return v
+
+    def load_state_dict(self, state):
+        """Set variables from {TF name: tensor}; creates missing ones."""
+        for k, t in state.items():
+            t = t.detach().to(self.device, torch.float32)
+            if k in self.vars:
+                with torch.no_grad():
+                    self.vars[k].copy_(t)
+            else:
+                if self.flat is not None:
+                    raise RuntimeError('ParamStore is already flattened')
+                self.vars[k] = t.clone().requires_grad_(True)
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.vars.items()}
+
+    def flatten(self):
+        """One flat parameter buffer + one flat gradient buffer; variables become views (TF name order)."""
+        if self.flat is not None:
+            return self.flat, self.flat_grad
+        names = sorted(self.vars)
+        n = sum(self.vars[k].numel() for k in names)
+        flat = torch.empty(n, dtype=torch.float32, device=self.device)
+        grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        for k in names:
+            v = self.vars[k]
+            m = v.numel()
+            flat[off:off + m].copy_(v.detach().reshape(-1))
+            nv = flat[off:off + m].view(v.shape).detach().requires_grad_(True)
+            nv.grad = grad[off:off + m].view(v.shape)
+            self.vars[k] = nv
+            off += m
+        self.flat, self.flat_grad = flat, grad
+        return flat, grad
+
+    def zero_grad(self):
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()
+        else:
+            for v in self.vars.values():
+                v.grad = None
+
+
+_DEFAULT_STORE = None
+
+
+def get_default_store():
+    global _DEFAULT_STORE
+    if _DEFAULT_STORE is None:
+        _DEFAULT_STORE = ParamStore()
+    return _DEFAULT_STORE
+
+
+def set_default_store(store):
+    global _DEFAULT_STORE
+    _DEFAULT_STORE = store
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# layer kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def same_pad(size, k, s):
+    """[TF1.4] SAME: out = ceil(size/s); total = max((out-1)*s + k - size, 0); before = total // 2."""
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return total // 2, total - total // 2
+
+
+_bn_ws = {}
+
+
+def _bn_workspace(device, channels):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    need = int(_b200.lib().lsi_b200_bn_workspace_bytes(max(channels, 1024)))
+    if key not in _bn_ws or _bn_ws[key].numel() < need:
+        _bn_ws[key] = torch.empty(need, dtype=torch.uint8, device=device)
+    return _bn_ws[key]
+
+
+def _conv(desc_kw, inp, w, out, bias=None):
+    d = _b200.ConvDesc(**desc_kw)
+    _b200.call('lsi_b200_conv2d', d, _b200.ptr(inp), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out), _b200.stream())
+
+
+def _wgrad(desc_kw, big, small, dw):
+    d = _b200.ConvDesc(**desc_kw)
+    _b200.call('lsi_b200_conv2d_wgrad', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
+
+
+class _Geometry(object):
+    """Descriptors of one layer: forward, data gradient, weight gradient."""
+
+    def __init__(self, transposed, B, Hi, Wi, Cin, Cout, k, s):
+        self.transposed, self.B, self.Hi, self.Wi, self.Cin, self.Cout, self.k, self.s = transposed, B, Hi, Wi, Cin, Cout, k, s
+        if not transposed:
+            self.Ho, self.Wo = -(-Hi // s), -(-Wi // s)
+            pt, pl = same_pad(Hi, k, s)[0], same_pad(Wi, k, s)[0]
+            if s > 1 and (Hi % s or Wi % s):
+                raise ValueError('stride-%d conv needs even input sizes, got %dx%d' % (s, Hi, Wi))
+            com = dict(batch=B, kh=k, kw=k, stride=s, pad_top=pt, pad_left=pl, epilogue=0, accumulate=0)
+            # weights [kh,kw,cin,cout]
+            self.fwd = dict(com, h_in=Hi, w_in=Wi, c_in=Cin, h_out=self.Ho, w_out=self.Wo, c_out=Cout, mode=0,
+                            w_tap_stride=Cin * Cout, w_ci_stride=Cout, w_co_stride=1, in_c_stride=Cin, out_c_stride=Cout)
+            self.dgrad = dict(com, h_in=self.Ho, w_in=self.Wo, c_in=Cout, h_out=Hi, w_out=Wi, c_out=Cin, mode=1,
+                              w_tap_stride=Cin * Cout, w_ci_stride=1, w_co_stride=Cout, in_c_stride=Cout, out_c_stride=Cin)
+            self.wgrad = dict(com, h_in=Hi, w_in=Wi, c_in=Cin, h_out=self.Ho, w_out=self.Wo, c_out=Cout, mode=0,
+                              w_tap_stride=0, w_ci_stride=0, w_co_stride=0, in_c_stride=Cin, out_c_stride=Cout)
+            self.w_shape = [k, k, Cin, Cout]
+        else:
+            assert (k, s) == (4, 2), 'only the 4x4 stride-2 up-convolution exists in the reference'
+            self.Ho, self.Wo = 2 * Hi, 2 * Wi
+            com = dict(batch=B, kh=4, kw=4, stride=2, pad_top=1, pad_left=1, epilogue=0, accumulate=0)
+            # weights [kh,kw,cout,cin]; forward = gradient of a SAME stride-2 conv from the 2x-sized side
+            self.fwd = dict(com, h_in=Hi, w_in=Wi, c_in=Cin, h_out=self.Ho, w_out=self.Wo, c_out=Cout, mode=1,
+                            w_tap_stride=Cin * Cout, w_ci_stride=1, w_co_stride=Cin, in_c_stride=Cin, out_c_stride=Cout)
+            self.dgrad = dict(com, h_in=self.Ho, w_in=self.Wo, c_in=Cout, h_out=Hi, w_out=Wi, c_out=Cin, mode=0,
+                              w_tap_stride=Cin * Cout, w_ci_stride=Cin, w_co_stride=1, in_c_stride=Cout, out_c_stride=Cin)
+            self.wgrad = dict(com, h_in=self.Ho, w_in=self.Wo, c_in=Cout, h_out=Hi, w_out=Wi, c_out=Cin, mode=0,
+                              w_tap_stride=0, w_ci_stride=0, w_co_stride=0, in_c_stride=Cout, out_c_stride=Cin)
+            self.w_shape = [4, 4, Cout, Cin]
+
+
+class _ConvBNReLU(torch.autograd.Function):
+    """slim.conv2d / slim.conv2d_transpose with normalizer_fn=batch_norm and activation relu (nets.py:263-272)."""
+
+    @staticmethod
+    def forward(ctx, x, w, beta, geo):
+        dev = x.device
+        z = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout, dtype=torch.float32, device=dev)
+        _conv(geo.fwd, x, w, z)
+        y = torch.empty_like(z)
+        stats = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+        P = geo.B * geo.Ho * geo.Wo
+        _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(y), _b200.ptr(stats), P, geo.Cout,
+                   geo.Cout, geo.Cout, BN_EPS, 1, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        ctx.save_for_backward(x, w, z, y, stats)
+        ctx.geo = geo
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, z, y, stats = ctx.saved_tensors
+        geo = ctx.geo
+        dev = x.device
+        dy = dy.contiguous()
+        P = geo.B * geo.Ho * geo.Wo
+        dz = torch.empty_like(z)
+        sums = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+        _b200.call('lsi_b200_bn_relu_backward', _b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
+                   _b200.ptr(sums), P, geo.Cout, geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0,
+                   _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        dbeta = sums[:, 0].contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _conv(geo.dgrad, dz, w, dx)
+        dw = torch.empty_like(w)
+        if geo.transposed:
+            _wgrad(geo.wgrad, dz, x, dw)
+        else:
+            _wgrad(geo.wgrad, x, dz, dw)
+        return dx, dw, dbeta, None
+
+
+class _ConvBiasSigmoid(torch.autograd.Function):
+    """The prediction conv: normalizer_fn=None, biases, activation sigmoid (nets.py:139-155)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, geo):
+        y = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout, dtype=torch.float32, device=x.device)
+        _conv(dict(geo.fwd, epilogue=2), x, w, y, bias)
+        ctx.save_for_backward(x, w, y)
+        ctx.geo = geo
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        geo = ctx.geo
+        dev = x.device
+        dy = dy.contiguous()
+        dz = torch.empty_like(y)
+        _b200.call('lsi_b200_sigmoid_backward', _b200.ptr(y), _b200.ptr(dy), _b200.ptr(dz), y.numel(), _b200.stream())
+        sums = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+        _b200.call('lsi_b200_channel_sums', _b200.ptr(dz), _b200.ptr(sums), geo.B * geo.Ho * geo.Wo, geo.Cout, geo.Cout,
+                   _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        dx = torch.empty_like(x)
+        _conv(geo.dgrad, dz, w, dx)
+        dw = torch.empty_like(w)
+        _wgrad(geo.wgrad, x, dz, dw)
+        return dx, dw, sums[:, 0].contiguous(), None
+
+
+class _ConcatChannels(torch.autograd.Function):
+    """tf.concat([a, b], axis=3) (nets.py:300,...) through the strided channel-copy kernel."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        B, H, W, Ca = a.shape
+        Cb = b.shape[3]
+        out = torch.empty(B, H, W, Ca + Cb, dtype=torch.float32, device=a.device)
+        P = B * H * W
+        _b200.call('lsi_b200_copy_channels', _b200.ptr(a), _b200.ptr(out), P, Ca, Ca, Ca + Cb, 0, _b200.stream())
+        _b200.call('lsi_b200_copy_channels', _b200.ptr(b), ctypes_offset(out, Ca), P, Cb, Cb, Ca + Cb, 0, _b200.stream())
+        ctx.dims = (B, H, W, Ca, Cb)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, Ca, Cb = ctx.dims
+        g = g.contiguous()
+        P = B * H * W
+        ga = torch.empty(B, H, W, Ca, dtype=torch.float32, device=g.device)
+        gb = torch.empty(B, H, W, Cb, dtype=torch.float32, device=g.device)
+        _b200.call('lsi_b200_copy_channels', _b200.ptr(g), _b200.ptr(ga), P, Ca, Ca + Cb, Ca, 0, _b200.stream())
+        _b200.call('lsi_b200_copy_channels', ctypes_offset(g, Ca), _b200.ptr(gb), P, Cb, Ca + Cb, Cb, 0, _b200.stream())
+        return ga, gb
+
+
+def ctypes_offset(t, n_floats):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + 4 * n_floats)
+
+
+def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False):
+    x = _b200.dev_f32(x, scope + ' input')
+    B, H, W, cin = x.shape
+    geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
+    w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+    beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+    return _ConvBNReLU.apply(x, w, beta, geo)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's public functions
+# ---------------------------------------------------------------------------------------------------------------------
+def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False, _scope='decoder', _store=None):
+    """nets.py:73-114 -- nconv x [4x4 s2 up-conv -> concat skip -> 3x3 conv].  Returns (feat, end_points)."""
+    _require_training(is_training)
+    store = _store or get_default_store()
+    n_filters = [32, 64, 128, 256] + [512] * max(nconv - 4, 0)
+    end_points = {}
+    for nc in range(nconv, 0, -1):
+        n_filt = n_filters[nc - 1]
+        feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True)
+        if nc > 1 and skip_feat is not None:
+            feat = _ConcatChannels.apply(feat, skip_feat[-nc + 1])
+        feat = _conv_layer(store, '%s/upcnv%db' % (_scope, nc), feat, n_filt, 3, 1, reuse)
+        end_points['%s/upcnv%db' % (_scope, nc)] = feat
+    return feat, end_points
+
+
+def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=None, reuse=False, is_training=True,
+                        _scope='pixelwise_pred', _store=None):
+    """nets.py:117-161 -- per layer its own decoder_simple, then a 3x3 conv + bias + sigmoid.  Returns
+    (preds [L,B,H,W,nc], end_points)."""
+    _require_training(is_training)
+    store = _store or get_default_store()
+    preds = []
+    for l in range(n_layers):
+        base = '%s/upsample_%d' % (_scope, l)
+        feat_l, _ = decoder_simple(feat, nconv=n_layerwise_steps, skip_feat=skip_feat, reuse=reuse, is_training=is_training,
+                                   _scope=base + '/decoder', _store=store)
+        B, H, W, cin = feat_l.shape
+        geo = _Geometry(False, B, H, W, cin, nc, 3, 1)
+        w = store.get('%s/pred_%d/weights' % (base, l), geo.w_shape, reuse, 'weights')
+        b = store.get('%s/pred_%d/biases' % (base, l), [nc], reuse, 'biases')
+        preds.append(_ConvBiasSigmoid.apply(feat_l, w, b, geo))
+    return torch.stack(preds, dim=0), {}
+
+
+def ldi_predictor(feat, n_layers=1, reuse=False, n_layerwise_steps=0, skip_feat=None, pred_masks=False, is_training=True,
+                  _store=None):
+    """nets.py:164-208.  Returns ldi = [textures [L,B,H,W,3], masks [L,B,H,W,1], disps [L,B,H,W,1]].  The textures and
+    disparities are channel views of the packed [L,B,H,W,nc] head output (no copy); with pred_masks=False the masks
+    are all ones and tagged so (the renderer and the losses then never read them)."""
+    nc = 3 + 1 + (1 if pred_masks else 0)
+    pred, _ = pixelwise_predictor(feat, nc=nc, n_layers=n_layers, n_layerwise_steps=n_layerwise_steps, skip_feat=skip_feat,
+                                  reuse=reuse, is_training=is_training, _scope='ldi_tex_disp/pixelwise_pred', _store=_store)
+    if pred_masks:
+        tex, masks, disps = pred[..., 0:3], pred[..., 3:4], pred[..., 4:5]
+        masks = nn_helpers.enforce_bg_occupied(torch.sigmoid(masks))      # sigmoid applied twice, as nets.py:143,202
+    else:
+        tex, disps = pred[..., 0:3], pred[..., 3:4]
+        masks = torch.ones(disps.shape, dtype=torch.float32, device=pred.device)
+        masks._lsi_all_ones = True
+    return [tex, masks, disps]
+
+
+def encoder_decoder_unet(inp_img, nz=1000, is_training=True, reuse=False, nl_diff_enc_dec=0, _store=None):
+    """nets.py:244-348.  Returns (feat, feat_dec, skip_feat, end_points) like the reference; `feat` (the FC features
+    the reference builds but never runs) is None.  H and W must be multiples of 128 (nets.py:298-300)."""
+    _require_training(is_training)
+    store = _store or get_default_store()
+    x = _b200.dev_f32(inp_img, 'inp_img')
+    if x.dim() != 4 or x.shape[3] != 3:
+        raise RuntimeError('lsi_b200: inp_img must be [B,H,W,3], got %s' % (tuple(x.shape),))
+    if x.shape[1] % 128 or x.shape[2] % 128:
+        raise ValueError('U-Net needs H and W to be multiples of 128 (nets.py:298-300), got %dx%d; see '
+                         'nets.pad_to_legal()' % (x.shape[1], x.shape[2]))
+    ep = {}
+    sc = 'encoder_decoder_unet'
+    for name, k, stride, cout in ENC:
+        x = _conv_layer(store, '%s/%s' % (sc, name), x, cout, k, stride, reuse)
+        ep[name] = x
+    skip_feat = [ep['cnv6b'], ep['cnv5b'], ep['cnv4b'], ep['cnv3b'], ep['cnv2b'], ep['cnv1b']]
+    feats_dec = []
+    feat = ep['cnv7b']
+    for k, cout, skip in DEC[:7 - nl_diff_enc_dec]:
+        up = _conv_layer(store, '%s/upcnv%d' % (sc, k), feat, cout, 4, 2, reuse, transposed=True)
+        if skip is not None:
+            up = _ConcatChannels.apply(up, ep[skip])
+        feat = _conv_layer(store, '%s/icnv%d' % (sc, k), up, cout, 3, 1, reuse)
+        ep['icnv%d' % k] = feat
+        feats_dec.append(feat)
+    return None, feats_dec[-1], skip_feat, ep
+
+
+def pad_to_legal(img):
+    """Policy for sizes the reference U-Net cannot run (64x64, 128x416, 256x832: BASELINE configs): zero-pad bottom/right
+    to the next multiple of 128 and crop the prediction back.  Returns (padded image, (H, W))."""
+    B, H, W, C = img.shape
+    Hp, Wp = -(-H // 128) * 128, -(-W // 128) * 128
+    if (Hp, Wp) == (H, W):
+        return img, (H, W)
+    out = torch.zeros(B, Hp, Wp, C, dtype=img.dtype, device=img.device)
+    out[:, :H, :W] = img
+    return out, (H, W)
+
+
+def _require_training(is_training):
+    if not is_training:
+        raise NotImplementedError('inference-mode batch norm: the reference never updates its moving averages '
+                                  '(train_utils.py:107-117) and evaluates with batch statistics (ldi_pred_eval.py:45)')

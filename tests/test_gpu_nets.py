@@ -1,0 +1,132 @@
+"""GPU parity tests of the CNN slice (pytest -m gpu): layers and the whole U-Net + heads against the CPU oracle
+(oracle/lsi_oracle_nets.py) and the fixture generated from the reference's own nets.py wiring."""
+import numpy as np
+import pytest
+import torch
+
+from _util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nets_mod():
+    assert torch.cuda.is_available()
+    from lsi.nnutils import nets
+    return nets
+
+
+@pytest.mark.parametrize('k,s,cin,cout,H,W,B', [
+    (7, 2, 3, 32, 16, 24, 2),      # stem: 3 input channels, asymmetric SAME padding (2,3)
+    (7, 1, 32, 32, 8, 12, 2),
+    (5, 2, 32, 64, 12, 8, 1),      # SAME padding (1,2)
+    (3, 2, 64, 128, 8, 8, 2),      # SAME padding (0,1)
+    (3, 1, 192, 128, 6, 10, 2),    # head concat layer
+    (3, 1, 40, 24, 5, 7, 3),       # ragged channel counts / sizes
+])
+def test_conv_bn_relu_layer(nets_mod, k, s, cin, cout, H, W, B):
+    from oracle import lsi_oracle_nets as N
+    torch.manual_seed(k * 100 + cin)
+    x = torch.randn(B, H, W, cin)
+    w = torch.randn(k, k, cin, cout) * (1.0 / (k * k * cin) ** 0.5)
+    beta = torch.randn(cout) * 0.3
+    g = torch.randn(B, -(-H // s), -(-W // s), cout)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, beta)]
+    ref = N.bn_relu(N.conv2d(leaves[0], leaves[1], s), leaves[2])
+    ref_g = torch.autograd.grad((ref * g).sum(), leaves)
+    store = nets_mod.ParamStore()
+    store.load_state_dict({'t/weights': w, 't/BatchNorm/beta': beta})
+    xg = x.cuda().requires_grad_(True)
+    out = nets_mod._conv_layer(store, 't', xg, cout, k, s, reuse=True)
+    got_g = torch.autograd.grad((out * g.cuda()).sum(), [xg, store.vars['t/weights'], store.vars['t/BatchNorm/beta']])
+    assert rel_err(out.detach().cpu(), ref.detach()) < 1e-4
+    for a, b, nme in zip(got_g, ref_g, ('dx', 'dw', 'dbeta')):
+        assert rel_err(a.cpu(), b) < 2e-4, nme
+
+
+@pytest.mark.parametrize('cin,cout,H,W,B', [(128, 64, 4, 6, 2), (512, 512, 1, 2, 2), (32, 32, 8, 8, 1), (24, 40, 3, 5, 2)])
+def test_upconv_bn_relu_layer(nets_mod, cin, cout, H, W, B):
+    from oracle import lsi_oracle_nets as N
+    torch.manual_seed(cin + cout)
+    x = torch.randn(B, H, W, cin)
+    w = torch.randn(4, 4, cout, cin) * (1.0 / (4 * cin) ** 0.5)
+    beta = torch.randn(cout) * 0.3
+    g = torch.randn(B, 2 * H, 2 * W, cout)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, beta)]
+    ref = N.bn_relu(N.conv2d_transpose(leaves[0], leaves[1]), leaves[2])
+    ref_g = torch.autograd.grad((ref * g).sum(), leaves)
+    store = nets_mod.ParamStore()
+    store.load_state_dict({'t/weights': w, 't/BatchNorm/beta': beta})
+    xg = x.cuda().requires_grad_(True)
+    out = nets_mod._conv_layer(store, 't', xg, cout, 4, 2, reuse=True, transposed=True)
+    got_g = torch.autograd.grad((out * g.cuda()).sum(), [xg, store.vars['t/weights'], store.vars['t/BatchNorm/beta']])
+    assert rel_err(out.detach().cpu(), ref.detach()) < 1e-4
+    for a, b, nme in zip(got_g, ref_g, ('dx', 'dw', 'dbeta')):
+        assert rel_err(a.cpu(), b) < 2e-4, nme
+
+
+def test_unet_and_heads_golden(nets_mod):
+    """Whole network at 128x128, L=2, B=2 against the fixture from the reference's wiring (fp64 evaluation as truth;
+    the reference's own fp32 evaluation is allowed the same distance)."""
+    from oracle import lsi_oracle_nets as N
+    g = load_golden('nets_unet_l2')
+    L, B, H, W, steps = (int(v) for v in g['meta'])
+    params = N.init_params(L, seed=int(g['param_seed']), n_layerwise_steps=steps, random_beta=True)
+    store = nets_mod.ParamStore()
+    store.load_state_dict(params)
+    img = torch.tensor(g['in_img'], device='cuda').requires_grad_(True)
+    _, feat_dec, skip_feat, _ = nets_mod.encoder_decoder_unet(img, nl_diff_enc_dec=steps, reuse=True, _store=store)
+    tex, masks, disps = nets_mod.ldi_predictor(feat_dec, n_layers=L, reuse=True, n_layerwise_steps=steps, skip_feat=skip_feat,
+                                               _store=store)
+    assert getattr(masks, '_lsi_all_ones', False) and float(masks.min()) == 1.0
+    pred = torch.cat([tex, disps * float(g['max_disp'])], dim=-1)
+    ref_noise = rel_err(g['pred_f32'], g['pred_f64'])
+    assert rel_err(feat_dec.detach().cpu()[:, ::2, ::2, ::4], g['feat_dec_f64']) < max(1e-3, 2 * rel_err(g['feat_dec_f32'], g['feat_dec_f64']))
+    assert rel_err(pred.detach().cpu()[:, :, ::4, ::4, :], g['pred_f64']) < max(1e-4, 2 * ref_noise)
+    g_pred = torch.tensor(np.random.RandomState(int(g['g_seed'])).normal(0, 1, (L, B, H, W, 4)).astype(np.float32), device='cuda')
+    names = sorted(store.vars)
+    assert names == [str(n) for n in g['grad_names']]
+    grads = torch.autograd.grad((pred * g_pred).sum(), [store.vars[n] for n in names] + [img])
+    assert rel_err(grads[-1].cpu()[:, ::4, ::4], g['d_img_f64']) < max(1e-3, 2 * rel_err(g['d_img_f32'], g['d_img_f64']))
+    for key in g:
+        if key.startswith('grad:') and key.endswith('_f64'):
+            nme = key[5:-4]
+            bar = max(1e-3, 2 * rel_err(g['grad:' + nme + '_f32'], g[key]))
+            assert rel_err(grads[names.index(nme)].cpu(), g[key]) < bar, nme
+    l2 = np.array([float(x.double().pow(2).sum().sqrt()) for x in grads[:-1]])
+    assert np.all(np.abs(l2 - g['grad_l2_f64']) <= 5e-3 * np.maximum(g['grad_l2_f64'], 1e-6))
+
+
+def test_unet_rejects_illegal_sizes_and_pads(nets_mod):
+    store = nets_mod.ParamStore()
+    with pytest.raises(ValueError, match='multiples of 128'):
+        nets_mod.encoder_decoder_unet(torch.rand(1, 64, 64, 3, device='cuda'), _store=store)
+    with pytest.raises(NotImplementedError):
+        nets_mod.encoder_decoder_unet(torch.rand(1, 128, 128, 3, device='cuda'), is_training=False, _store=store)
+    padded, (h, w) = nets_mod.pad_to_legal(torch.rand(1, 64, 200, 3, device='cuda'))
+    assert padded.shape == (1, 128, 256, 3) and (h, w) == (64, 200)
+
+
+def test_param_store_flatten_and_adam(nets_mod):
+    """Flat parameter/gradient buffers and the fused Adam step against torch.optim.Adam semantics restated for TF
+    (epsilon outside the square root, lr_t = lr*sqrt(1-b2^t)/(1-b1^t))."""
+    from lsi import _b200
+    store = nets_mod.ParamStore()
+    a = store.get('a/weights', [3, 3, 4, 8], False, 'weights')
+    b = store.get('a/BatchNorm/beta', [8], False, 'beta')
+    flat, grad = store.flatten()
+    assert flat.numel() == 3 * 3 * 4 * 8 + 8
+    (store.vars['a/weights'].sum() * 2 + (store.vars['a/BatchNorm/beta'] * 3).sum()).backward()
+    assert torch.all(grad[:8] == 3) and torch.all(grad[8:] == 2)        # sorted names: beta first
+    p0 = flat.clone()
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    lr, b1, b2, eps = 1e-4, 0.9, 0.999, 1e-8
+    for step in (1, 2, 3):
+        _b200.call('lsi_b200_adam_step', _b200.ptr(flat), _b200.ptr(grad), _b200.ptr(m), _b200.ptr(v), flat.numel(), lr, b1, b2,
+                   eps, step, 1.0, _b200.stream())
+    gm, gv, ref = torch.zeros_like(p0), torch.zeros_like(p0), p0.clone()
+    for step in (1, 2, 3):
+        gm = b1 * gm + (1 - b1) * grad
+        gv = b2 * gv + (1 - b2) * grad * grad
+        ref -= lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step) * gm / (gv.sqrt() + eps)
+    assert rel_err(flat.cpu(), ref.cpu()) < 1e-6
