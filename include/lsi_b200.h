@@ -184,6 +184,16 @@ LSI_B200_API int lsi_b200_conv2d(const lsi_b200_conv_desc* d, const float* in, c
 LSI_B200_API int lsi_b200_conv2d_wgrad(const lsi_b200_conv_desc* d, const float* big, const float* small, float* dw,
                                        void* stream);
 
+/* Tensor-core (tcgen05 + TMA, TF32 inputs / fp32 accumulate) version of lsi_b200_conv2d for layers whose summed
+ * channel count is a multiple of 32, with an optional second input source that implements tf.concat on the fly:
+ * channels [0, c_in_a) come from in_a (pixel stride d->in_c_stride), [c_in_a, c_in) from in_b (pixel stride
+ * in_b_c_stride; NULL when c_in_a == c_in).  workspace: lsi_b200_conv2d_tc_workspace_bytes(d). */
+LSI_B200_API int lsi_b200_conv2d_tc_supported(const lsi_b200_conv_desc* d, int c_in_a);
+LSI_B200_API size_t lsi_b200_conv2d_tc_workspace_bytes(const lsi_b200_conv_desc* d);
+LSI_B200_API int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
+                                    int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* slim.batch_norm(is_training=True, center=True, scale=False) + ReLU (nets.py:263-272): batch statistics over the
  * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward.  workspace:
  * lsi_b200_bn_workspace_bytes(channels). */

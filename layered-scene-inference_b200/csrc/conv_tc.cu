@@ -1,0 +1,362 @@
+// Tensor-core convolution for B200 (sm_100a): implicit GEMM on tcgen05 with TMA-fed shared-memory operands and
+// TMEM accumulators.  Same descriptor and semantics as lsi_b200_conv2d (conv.cu), used for every layer whose summed
+// channel count is a multiple of 32 -- i.e. everything but the 3-channel stem (nets.py:273).
+//
+//   GEMM view   D[128 pixels x N channels] += A[128 x K] * B[N x K]^T,  K = taps x Cin, fp32 data fed as TF32
+//   A operand   activations, NHWC fp32.  A CTA owns an 8 x 16 patch of output pixels of one image; for tap (ky,kx) and
+//               channel chunk c0 the im2col tile is the same patch shifted by the tap, i.e. ONE 4-D TMA box
+//               (32 ch x 16 x 8 x 1) whose out-of-bounds elements TMA zero-fills (= TF SAME padding, asymmetric or
+//               not); stride-2 convs use the tensor map's element strides; the 4x4 stride-2 up-convolution and conv
+//               data gradients run phase-decomposed (4 valid taps per output phase).  Two tensor maps implement the
+//               channel concat of the U-Net skip connections without materialising it.
+//   B operand   weights re-laid out once per call as [tap][N_pad][Cin] (K-major) by a small kernel, 2-D TMA box.
+//   shared mem  128-byte rows with the 128B swizzle (TMA writes it, the UMMA descriptors read it), 4-stage
+//               full/empty mbarrier ring;  warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+//               warps 2-5 = epilogue (tcgen05.ld -> bias/sigmoid/accumulate -> 128-bit global stores).
+//   accumulate  TMEM, 128 lanes x N fp32 columns.
+#include <cuda.h>
+
+#include "capi_common.h"
+#include "common.cuh"
+
+namespace lsi {
+
+constexpr int kTileH = 8, kTileW = 16, kTileM = kTileH * kTileW;   // 128 output pixels = 128 TMEM lanes
+constexpr int kKC = 32;                                            // fp32 channels per K chunk = one 128-byte row
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+struct TcParams {
+  float* out; const float* bias;
+  int Ho, Wo, Co, out_cs;
+  int Hp, Wp;                 // per-phase output extent
+  int tiles_x, tiles_y;       // patches per image (phase space)
+  int Ca, Cb;                 // channels of source A / source B (concat), Cb may be 0
+  int kh, kw, stride, pad_t, pad_l, mode;
+  int n_tile, n_pad;          // UMMA N, padded Cout
+  int epilogue, accumulate;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);         // start address
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.n_tile * 128;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = (p.mode == 1) ? p.stride : 1;
+  const int py = (p.mode == 1) ? (int)blockIdx.z / s : 0, px = (p.mode == 1) ? (int)blockIdx.z % s : 0;
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; const int n_img = t / p.tiles_y;
+  const int y0 = ty * kTileH, x0 = tx * kTileW;       // patch origin in phase space
+  const int n0 = blockIdx.y * p.n_tile;
+
+  const int ky0 = (p.mode == 1) ? ((py + p.pad_t) % s) : 0, kx0 = (p.mode == 1) ? ((px + p.pad_l) % s) : 0;
+  const int nky = (p.kh - ky0 + s - 1) / s, nkx = (p.kw - kx0 + s - 1) / s;
+  const int chunks = (p.Ca + p.Cb) / kKC;
+  const int k_iters = nky * nkx * chunks;
+
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.n_tile) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int it = 0; it < k_iters; ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        const int tap = it / chunks, c0 = (it - tap * chunks) * kKC;
+        const int ky = ky0 + (tap / nkx) * s, kx = kx0 + (tap % nkx) * s;
+        int ys, xs;
+        if (p.mode == 0) { ys = y0 * p.stride - p.pad_t + ky; xs = x0 * p.stride - p.pad_l + kx; }
+        else { ys = y0 + (py + p.pad_t - ky) / s; xs = x0 + (px + p.pad_l - kx) / s; }   // exact: tap list matches the phase
+        uint8_t* sa = smem + st * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full[st], a_bytes + b_bytes);
+        if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs, ys, n_img);
+        else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs, ys, n_img);
+        tma_load_2d(sb, &map_w, &full[st], c0, (ky * p.kw + kx) * p.n_pad + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      for (int it = 0; it < k_iters; ++it) {
+        const int st = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + a_bytes;
+#pragma unroll
+        for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+          umma_tf32(tmem_base, umma_desc(sa + kk * 32), umma_desc(sb + kk * 32), idesc, (it | kk) != 0);
+        }
+        umma_commit(&empty[st]);                 // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);                    // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lg = warp & 3;                     // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;              // = A tile row = pixel within the patch
+    const int hy = row / kTileW, wx = row % kTileW;
+    int oy = y0 + hy, ox = x0 + wx;
+    const bool in_range = oy < p.Hp && ox < p.Wp;
+    if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
+    float* dst = p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + n0;
+    for (int c = 0; c < p.n_tile; c += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c;
+      if (p.n_tile - c >= 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+      } else {   // n_tile == 16
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (in_range) {
+        const int nvalid = min(min(32, p.n_tile - c), p.Co - (n0 + c));
+        if (nvalid == 32 && p.epilogue == 0 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst + c) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nvalid) {
+              float v = __uint_as_float(r[j]);
+              if (p.epilogue >= 1) v += __ldg(p.bias + n0 + c + j);
+              if (p.epilogue == 2) v = 1.f / (1.f + expf(-v));
+              if (p.accumulate) v += dst[c + j];
+              dst[c + j] = v;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// weights (any strides) -> [tap][n_pad][cin] fp32, zero rows for co >= Cout
+__global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wk, int taps, int cin,
+                                                           int cout, int n_pad, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * n_pad * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % n_pad);
+    const int tap = (int)(i / ((long long)cin * n_pad));
+    wk[i] = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace lsi
+
+using namespace lsi;
+
+extern "C" size_t lsi_b200_conv2d_tc_workspace_bytes(const lsi_b200_conv_desc* d) {
+  if (!d) return 0;
+  const size_t n_pad = (size_t)(d->c_out + 15) / 16 * 16;
+  return (size_t)d->kh * d->kw * n_pad * (size_t)d->c_in * sizeof(float) + 256;
+}
+
+extern "C" int lsi_b200_conv2d_tc_supported(const lsi_b200_conv_desc* d, int c_in_a) {
+  if (!d) return 0;
+  if (d->c_in % kKC != 0 || c_in_a % kKC != 0 || c_in_a > d->c_in || c_in_a < 1) return 0;
+  if (d->stride < 1 || d->stride > 2 || (d->mode != 0 && d->mode != 1)) return 0;
+  if (d->mode == 1 && (d->h_out % d->stride || d->w_out % d->stride)) return 0;
+  if (d->in_c_stride % 4 != 0) return 0;
+  const int n_pad = (d->c_out + 15) / 16 * 16;
+  int n_tile = n_pad <= 128 ? n_pad : 128;
+  if (n_pad > 128 && n_pad % 128 != 0) n_tile = 64;
+  if (n_pad % n_tile != 0 || !(n_tile == 16 || n_tile % 32 == 0)) return 0;
+  return 1;
+}
+
+// Same contract as lsi_b200_conv2d, plus an optional second input source: channels [0, c_in_a) come from `in_a`
+// (pixel stride in_c_stride), channels [c_in_a, c_in) from `in_b` (pixel stride in_b_c_stride) -- tf.concat on the fly.
+extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
+                                  int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  LSI_REQUIRE(d && in_a && w && out && workspace, "NULL pointer argument");
+  LSI_REQUIRE(lsi_b200_conv2d_tc_supported(d, c_in_a), "shape not supported by the tensor-core path");
+  LSI_REQUIRE(c_in_a == d->c_in || (in_b && in_b_c_stride % 4 == 0 && in_b_c_stride >= d->c_in - c_in_a), "bad second source");
+  LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
+  LSI_REQUIRE(workspace_bytes >= lsi_b200_conv2d_tc_workspace_bytes(d), "workspace too small");
+  LSI_REQUIRE(((uintptr_t)in_a & 15) == 0 && (!in_b || ((uintptr_t)in_b & 15) == 0), "inputs must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode();
+  LSI_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cudaStream_t st = as_stream(stream);
+
+  TcParams p;
+  p.out = out; p.bias = bias; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
+  const int s = d->mode == 1 ? d->stride : 1;
+  p.Hp = d->h_out / s; p.Wp = d->w_out / s;
+  p.tiles_x = (p.Wp + kTileW - 1) / kTileW; p.tiles_y = (p.Hp + kTileH - 1) / kTileH;
+  p.Ca = c_in_a; p.Cb = d->c_in - c_in_a;
+  p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
+  p.n_pad = (d->c_out + 15) / 16 * 16;
+  p.n_tile = p.n_pad <= 128 ? p.n_pad : 128;
+  if (p.n_pad > 128 && p.n_pad % 128 != 0) p.n_tile = 64;
+  LSI_REQUIRE(p.n_pad % p.n_tile == 0 && (p.n_tile == 16 || p.n_tile % 32 == 0), "unsupported output channel count %d", d->c_out);
+  p.epilogue = d->epilogue; p.accumulate = d->accumulate;
+
+  // weights -> K-major [tap][n_pad][cin]
+  float* wk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  const int taps = d->kh * d->kw;
+  {
+    const long long total = (long long)taps * p.n_pad * d->c_in;
+    long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+    prep_weights_kernel<<<(unsigned)g, 256, 0, st>>>(w, wk, taps, d->c_in, d->c_out, p.n_pad, d->w_tap_stride, d->w_ci_stride,
+                                                     d->w_co_stride);
+    LSI_LAUNCH_CHECK();
+  }
+
+  // tensor maps
+  auto make_act_map = [&](CUtensorMap* m, const float* base, int channels, int cs) -> int {
+    const int es = (d->mode == 0) ? d->stride : 1;      // element (traversal) stride of the gather
+    cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)d->w_in * cs * 4, (cuuint64_t)d->h_in * d->w_in * cs * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((kTileW - 1) * es + 1), (cuuint32_t)((kTileH - 1) * es + 1), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return LSI_B200_ECUDA; }
+    return LSI_B200_OK;
+  };
+  CUtensorMap map_a, map_b, map_w;
+  if (int rc = make_act_map(&map_a, in_a, p.Ca, d->in_c_stride)) return rc;
+  if (p.Cb > 0) { if (int rc = make_act_map(&map_b, in_b, p.Cb, in_b_c_stride)) return rc; }
+  else map_b = map_a;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * p.n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)p.n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
+  }
+  const uint32_t b_bytes = ((uint32_t)p.n_tile * 128 + 1023) & ~1023u;
+  const size_t smem = (size_t)kStages * (kTileM * 128 + b_bytes) + 256 + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * d->batch), (unsigned)(p.n_pad / p.n_tile), (unsigned)(s * s));
+  conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}

@@ -1,0 +1,92 @@
+"""GPU: the tcgen05/TMA convolution (lsi_b200_conv2d_tc) against the fp32 CUDA-core kernel (lsi_b200_conv2d) that is
+itself checked against the CPU oracle in tests/test_gpu_nets.py.  TF32 inputs, fp32 accumulation: tolerance 2e-3 of
+the output scale."""
+import ctypes
+
+import pytest
+import torch
+
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def _run_both(B, Hi, Wi, Cin, Cout, k, s, mode, transposed_weights, split=None, epilogue=0, accumulate=0, seed=0):
+    from lsi import _b200
+    from lsi.nnutils.nets import same_pad
+    lib = _b200.lib()
+    torch.manual_seed(seed)
+    dev = 'cuda'
+    if mode == 0:
+        Ho, Wo = -(-Hi // s), -(-Wi // s)
+        pt, pl = same_pad(Hi, k, s)[0], same_pad(Wi, k, s)[0]
+    else:
+        Ho, Wo = Hi * s, Wi * s
+        pt = pl = 1 if s == 2 else same_pad(Ho, k, 1)[0]
+    x = torch.randn(B, Hi, Wi, Cin, device=dev)
+    if transposed_weights:     # [kh,kw,cout,cin]
+        w = torch.randn(k, k, Cout, Cin, device=dev) / (k * k * Cin) ** 0.5
+        ws = dict(w_tap_stride=Cin * Cout, w_ci_stride=1, w_co_stride=Cin)
+    else:                      # [kh,kw,cin,cout]
+        w = torch.randn(k, k, Cin, Cout, device=dev) / (k * k * Cin) ** 0.5
+        ws = dict(w_tap_stride=Cin * Cout, w_ci_stride=Cout, w_co_stride=1)
+    bias = torch.randn(Cout, device=dev)
+    kw = dict(batch=B, h_in=Hi, w_in=Wi, c_in=Cin, h_out=Ho, w_out=Wo, c_out=Cout, kh=k, kw=k, stride=s, pad_top=pt,
+              pad_left=pl, mode=mode, in_c_stride=Cin, out_c_stride=Cout, epilogue=epilogue, accumulate=accumulate, **ws)
+    d = _b200.ConvDesc(**kw)
+    init = torch.randn(B, Ho, Wo, Cout, device=dev)
+    ref = init.clone()
+    _b200.call('lsi_b200_conv2d', d, _b200.ptr(x), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(ref), _b200.stream())
+    out = init.clone()
+    ca = Cin if split is None else split
+    assert lib.lsi_b200_conv2d_tc_supported(d, ca) == 1
+    nws = lib.lsi_b200_conv2d_tc_workspace_bytes(d)
+    wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
+    if split is None:
+        _b200.call('lsi_b200_conv2d_tc', d, _b200.ptr(x), Cin, None, 0, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out),
+                   _b200.ptr(wsb), nws, _b200.stream())
+    else:                      # concat on the fly: two separately allocated sources
+        xa, xb = x[..., :split].contiguous(), x[..., split:].contiguous()
+        d2 = _b200.ConvDesc(**dict(kw, in_c_stride=split))
+        _b200.call('lsi_b200_conv2d_tc', d2, _b200.ptr(xa), split, _b200.ptr(xb), Cin - split, _b200.ptr(w), _b200.ptr(bias),
+                   _b200.ptr(out), _b200.ptr(wsb), nws, _b200.stream())
+    torch.cuda.synchronize()
+    return out, ref
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k', [
+    (1, 8, 16, 32, 32, 3),        # exactly one tile
+    (2, 16, 32, 64, 64, 3),
+    (1, 11, 21, 32, 128, 3),      # ragged spatial size: partial tiles, zero-filled halo
+    (2, 8, 16, 96, 64, 3),        # head layer upcnv2b
+    (1, 8, 16, 192, 128, 3),      # head layer upcnv3b
+    (1, 8, 16, 32, 4, 3),         # prediction conv: Cout padded to 16
+    (1, 8, 16, 32, 32, 7),        # cnv1b
+    (1, 8, 16, 64, 64, 5),        # cnv2b
+    (1, 4, 6, 1024, 512, 3),      # icnv7: four N tiles
+])
+def test_conv_stride1(B, H, W, Cin, Cout, k):
+    out, ref = _run_both(B, H, W, Cin, Cout, k, 1, 0, False)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+def test_conv_concat_on_the_fly_bias_sigmoid_accumulate():
+    out, ref = _run_both(2, 8, 16, 96, 64, 3, 1, 0, False, split=64)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+    out, ref = _run_both(1, 8, 16, 32, 4, 3, 1, 0, False, epilogue=2)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+    out, ref = _run_both(1, 8, 16, 64, 32, 3, 1, 0, False, accumulate=1)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(1, 4, 8, 128, 64), (2, 8, 16, 64, 32), (1, 5, 9, 128, 128)])
+def test_upconv_phase_decomposed(B, H, W, Cin, Cout):
+    out, ref = _run_both(B, H, W, Cin, Cout, 4, 2, 1, True)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k', [(1, 16, 32, 32, 64, 5), (2, 16, 32, 64, 128, 3), (1, 32, 64, 32, 32, 7)])
+def test_conv_stride2_element_strides(B, H, W, Cin, Cout, k):
+    out, ref = _run_both(B, H, W, Cin, Cout, k, 2, 0, False)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
