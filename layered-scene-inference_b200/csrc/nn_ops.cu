@@ -66,13 +66,16 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const StatParams p) 
   }
 }
 
-// forward: stats[c] = (mean, rsqrt(var + eps)); backward: stats_out[c] = (sum dz, sum dz*xhat)
-__global__ void finalize_stats_kernel(const double* __restrict__ partial, int nblk, int C, long long P, float eps, int mode,
-                                      float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// forward: stats[c] = (mean, rsqrt(var + eps)); backward: stats_out[c] = (sum dz, sum dz*xhat).  One warp per channel.
+__global__ void __launch_bounds__(256) finalize_stats_kernel(const double* __restrict__ partial, int nblk, int C, long long P,
+                                                             float eps, int mode, float* __restrict__ out) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblk; ++i) { a += partial[((size_t)i * C + c) * 2]; b += partial[((size_t)i * C + c) * 2 + 1]; }
+  for (int i = lane; i < nblk; i += 32) { a += partial[((size_t)i * C + c) * 2]; b += partial[((size_t)i * C + c) * 2 + 1]; }
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane != 0) return;
   if (mode == 0) {
     const double mean = a / (double)P;
     double var = b / (double)P - mean * mean;
@@ -95,6 +98,25 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
     float v = (p.x[q * p.x_cs + c] - __ldg(p.stats + 2 * c)) * __ldg(p.stats + 2 * c + 1) + __ldg(p.beta + c);
     if (p.relu) v = fmaxf(v, 0.f);
     p.y[q * p.y_cs + c] = v;
+  }
+}
+
+// dense fast path (x_cs == y_cs == C, C % 4 == 0, 16-byte aligned): 128-bit loads/stores, 32-bit channel arithmetic
+__global__ void __launch_bounds__(256) bn_apply_vec4_kernel(const BnApplyParams p) {
+  const long long total4 = p.P * p.C / 4;
+  const unsigned c4n = (unsigned)p.C / 4;
+  const float4* x = reinterpret_cast<const float4*>(p.x);
+  float4* y = reinterpret_cast<float4*>(p.y);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((unsigned long long)i % c4n) * 4;
+    const float4 v = __ldcs(x + i);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.stats + 2 * c)), s1 = __ldg(reinterpret_cast<const float4*>(p.stats + 2 * c) + 1);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+    float4 o;
+    o.x = (v.x - s0.x) * s0.y + b.x; o.y = (v.y - s0.z) * s0.w + b.y;
+    o.z = (v.z - s1.x) * s1.y + b.z; o.w = (v.w - s1.z) * s1.w + b.w;
+    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    y[i] = o;
   }
 }
 
@@ -186,10 +208,14 @@ extern "C" int lsi_b200_bn_relu_forward(const float* x, const float* beta, float
   StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
   channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
   LSI_LAUNCH_CHECK();
-  finalize_stats_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, eps, 0, stats);
+  finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, eps, 0, stats);
   LSI_LAUNCH_CHECK();
   BnApplyParams ap{x, stats, beta, y, n_pixels, channels, x_c_stride, y_c_stride, relu};
-  bn_apply_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(ap);
+  if (x_c_stride == channels && y_c_stride == channels && channels % 4 == 0 && ((uintptr_t)x & 15) == 0 &&
+      ((uintptr_t)y & 15) == 0 && ((uintptr_t)beta & 15) == 0)
+    bn_apply_vec4_kernel<<<ew_grid(n_pixels * channels / 4), 256, 0, st>>>(ap);
+  else
+    bn_apply_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(ap);
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }
@@ -205,7 +231,7 @@ extern "C" int lsi_b200_bn_relu_backward(const float* x, const float* y, const f
   StatParams sp{x, y, dy, stats, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, 1, relu};
   channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
   LSI_LAUNCH_CHECK();
-  finalize_stats_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, dbeta_sums);
+  finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, dbeta_sums);
   LSI_LAUNCH_CHECK();
   BnBwdParams bp{x, y, dy, stats, dbeta_sums, dx, n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, dx_c_stride, relu, accumulate};
   bn_backward_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(bp);
@@ -223,7 +249,7 @@ extern "C" int lsi_b200_channel_sums(const float* x, float* sums, long long n_pi
   StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
   channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
   LSI_LAUNCH_CHECK();
-  finalize_stats_kernel<<<(channels + 127) / 128, 128, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, sums);
+  finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, sums);
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }

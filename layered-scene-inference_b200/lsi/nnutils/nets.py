@@ -147,8 +147,42 @@ def _bn_workspace(device, channels):
     return _bn_ws[key]
 
 
+_CONV_MODE = 'tf32'
+
+
+def set_conv_mode(mode):
+    """'tf32' (default): tcgen05 tensor-core kernels (TF32 inputs, fp32 accumulation) wherever the layer shape allows,
+    fp32 CUDA-core kernels elsewhere (the 3-channel stem, weight gradients).  'fp32': CUDA-core kernels everywhere --
+    the bit-for-bit-reproducible-arithmetic mode the 1e-4 parity tests of the CNN run in."""
+    global _CONV_MODE
+    if mode not in ('tf32', 'fp32'):
+        raise ValueError(mode)
+    _CONV_MODE = mode
+
+
+def get_conv_mode():
+    return _CONV_MODE
+
+
+_tc_ws = {}
+
+
+def _tc_workspace(device, nbytes):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    if key not in _tc_ws or _tc_ws[key].numel() < nbytes:
+        _tc_ws[key] = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+    return _tc_ws[key]
+
+
 def _conv(desc_kw, inp, w, out, bias=None):
     d = _b200.ConvDesc(**desc_kw)
+    lib = _b200.lib()
+    if _CONV_MODE == 'tf32' and lib.lsi_b200_conv2d_tc_supported(d, d.c_in) == 1 and inp.data_ptr() % 16 == 0:
+        nws = int(lib.lsi_b200_conv2d_tc_workspace_bytes(d))
+        ws = _tc_workspace(inp.device, nws)
+        _b200.call('lsi_b200_conv2d_tc', d, _b200.ptr(inp), d.c_in, None, 0, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out),
+                   _b200.ptr(ws), ws.numel(), _b200.stream())
+        return
     _b200.call('lsi_b200_conv2d', d, _b200.ptr(inp), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out), _b200.stream())
 
 

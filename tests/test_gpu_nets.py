@@ -9,11 +9,34 @@ from _util import load_golden, rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope='module')
-def nets_mod():
+@pytest.fixture(scope='module', params=['fp32', 'tf32'])
+def nets_mod(request):
+    """Every test runs in both arithmetic modes: 'fp32' (CUDA-core kernels, 1e-4 class parity) and 'tf32' (tcgen05
+    tensor-core kernels; TF32 has a 10-bit mantissa, so the bars are multiplied by TF32_SLACK)."""
     assert torch.cuda.is_available()
     from lsi.nnutils import nets
-    return nets
+    nets.set_conv_mode(request.param)
+    yield nets
+    nets.set_conv_mode('tf32')
+
+
+def _slack(nets_mod):
+    return 1.0 if nets_mod.get_conv_mode() == 'fp32' else 100.0
+
+
+def _check(nets_mod, got, ref, tol, what):
+    """fp32 mode: max error within tol of the tensor scale.  tf32 mode: a TF32-sized perturbation flips ReLU masks
+    (y near 0) and with them whole gradient contributions, so the max error of a gradient is O(1) at isolated elements;
+    the check is on the bulk instead: 97 % of the elements within 100*tol, relative L2 error below 3e-2."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if nets_mod.get_conv_mode() == 'fp32':
+        assert rel_err(got, ref) < tol, what
+        return
+    scale = max(np.abs(ref).max(), 1e-30)
+    frac = float((np.abs(got - ref) / scale > 100 * tol).mean())
+    l2 = float(np.sqrt(((got - ref) ** 2).sum()) / max(np.sqrt((ref ** 2).sum()), 1e-30))
+    assert frac <= 0.03 and l2 < 3e-2, '%s: %.3g of elements beyond %g, relative L2 error %.3g' % (what, frac, 100 * tol, l2)
 
 
 @pytest.mark.parametrize('k,s,cin,cout,H,W,B', [
@@ -39,9 +62,9 @@ def test_conv_bn_relu_layer(nets_mod, k, s, cin, cout, H, W, B):
     xg = x.cuda().requires_grad_(True)
     out = nets_mod._conv_layer(store, 't', xg, cout, k, s, reuse=True)
     got_g = torch.autograd.grad((out * g.cuda()).sum(), [xg, store.vars['t/weights'], store.vars['t/BatchNorm/beta']])
-    assert rel_err(out.detach().cpu(), ref.detach()) < 1e-4
+    _check(nets_mod, out.detach().cpu(), ref.detach(), 1e-4, 'y')
     for a, b, nme in zip(got_g, ref_g, ('dx', 'dw', 'dbeta')):
-        assert rel_err(a.cpu(), b) < 2e-4, nme
+        _check(nets_mod, a.cpu(), b, 2e-4, nme)
 
 
 @pytest.mark.parametrize('cin,cout,H,W,B', [(128, 64, 4, 6, 2), (512, 512, 1, 2, 2), (32, 32, 8, 8, 1), (24, 40, 3, 5, 2)])
@@ -60,14 +83,16 @@ def test_upconv_bn_relu_layer(nets_mod, cin, cout, H, W, B):
     xg = x.cuda().requires_grad_(True)
     out = nets_mod._conv_layer(store, 't', xg, cout, 4, 2, reuse=True, transposed=True)
     got_g = torch.autograd.grad((out * g.cuda()).sum(), [xg, store.vars['t/weights'], store.vars['t/BatchNorm/beta']])
-    assert rel_err(out.detach().cpu(), ref.detach()) < 1e-4
+    _check(nets_mod, out.detach().cpu(), ref.detach(), 1e-4, 'y')
     for a, b, nme in zip(got_g, ref_g, ('dx', 'dw', 'dbeta')):
-        assert rel_err(a.cpu(), b) < 2e-4, nme
+        _check(nets_mod, a.cpu(), b, 2e-4, nme)
 
 
 def test_unet_and_heads_golden(nets_mod):
     """Whole network at 128x128, L=2, B=2 against the fixture from the reference's wiring (fp64 evaluation as truth;
-    the reference's own fp32 evaluation is allowed the same distance)."""
+    the reference's own fp32 evaluation is allowed the same distance).  In tf32 mode this is an integration check only:
+    20 TF32 layers with batch-stat BN over as few as 2 samples (the 1x1 bottleneck at this size) drift by ~2e-2 at the
+    sigmoid outputs, so the bars are 100x wider there."""
     from oracle import lsi_oracle_nets as N
     g = load_golden('nets_unet_l2')
     L, B, H, W, steps = (int(v) for v in g['meta'])
@@ -81,20 +106,24 @@ def test_unet_and_heads_golden(nets_mod):
     assert getattr(masks, '_lsi_all_ones', False) and float(masks.min()) == 1.0
     pred = torch.cat([tex, disps * float(g['max_disp'])], dim=-1)
     ref_noise = rel_err(g['pred_f32'], g['pred_f64'])
-    assert rel_err(feat_dec.detach().cpu()[:, ::2, ::2, ::4], g['feat_dec_f64']) < max(1e-3, 2 * rel_err(g['feat_dec_f32'], g['feat_dec_f64']))
-    assert rel_err(pred.detach().cpu()[:, :, ::4, ::4, :], g['pred_f64']) < max(1e-4, 2 * ref_noise)
+    k = _slack(nets_mod)
+    _check(nets_mod, feat_dec.detach().cpu()[:, ::2, ::2, ::4], g['feat_dec_f64'], max(1e-3, 2 * rel_err(g['feat_dec_f32'], g['feat_dec_f64'])), 'feat_dec')
+    _check(nets_mod, pred.detach().cpu()[:, :, ::4, ::4, :], g['pred_f64'], max(1e-4, 2 * ref_noise), 'pred')
     g_pred = torch.tensor(np.random.RandomState(int(g['g_seed'])).normal(0, 1, (L, B, H, W, 4)).astype(np.float32), device='cuda')
     names = sorted(store.vars)
     assert names == [str(n) for n in g['grad_names']]
     grads = torch.autograd.grad((pred * g_pred).sum(), [store.vars[n] for n in names] + [img])
-    assert rel_err(grads[-1].cpu()[:, ::4, ::4], g['d_img_f64']) < max(1e-3, 2 * rel_err(g['d_img_f32'], g['d_img_f64']))
+    if nets_mod.get_conv_mode() == 'fp32':
+        assert rel_err(grads[-1].cpu()[:, ::4, ::4], g['d_img_f64']) < max(1e-3, 2 * rel_err(g['d_img_f32'], g['d_img_f64']))
     for key in g:
         if key.startswith('grad:') and key.endswith('_f64'):
             nme = key[5:-4]
             bar = max(1e-3, 2 * rel_err(g['grad:' + nme + '_f32'], g[key]))
-            assert rel_err(grads[names.index(nme)].cpu(), g[key]) < bar, nme
+            if nets_mod.get_conv_mode() == 'fp32':
+                assert rel_err(grads[names.index(nme)].cpu(), g[key]) < bar, nme
     l2 = np.array([float(x.double().pow(2).sum().sqrt()) for x in grads[:-1]])
-    assert np.all(np.abs(l2 - g['grad_l2_f64']) <= 5e-3 * np.maximum(g['grad_l2_f64'], 1e-6))
+    # tf32 mode: the gradient norms of all 72 variables stay within 30 % (ReLU-mask flips through ~20 layers); fp32: 0.5 %
+    assert np.all(np.abs(l2 - g['grad_l2_f64']) <= (5e-3 if k == 1.0 else 0.3) * np.maximum(g['grad_l2_f64'], 1e-6))
 
 
 def test_unet_rejects_illegal_sizes_and_pads(nets_mod):
