@@ -1,15 +1,16 @@
 #!/usr/bin/env python
-"""bench.py -- rendered views/sec of the B200-native LDI renderer at BASELINE.json's headline configuration
-(256x832, 4-layer LDI, batch 64 per GPU), with the splat kernel's HBM roofline, the reference CPU path timed on
-the box's host cores, and the end-to-end (host buffers in/out) number.
+"""bench.py -- rendered views/sec of the B200-native LDI view-synthesis path at BASELINE.json's headline configuration
+(256x832, 4-layer LDI, batch 64 per GPU): encoder-decoder CNN -> per-layer (texture, disparity) -> forward-splat
+renderer, with the splat kernel's HBM roofline, the conv kernels' tensor throughput, the reference CPU path timed on
+the box's host cores, and the end-to-end (host images in, rendered views out) number.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" = one pass of the renderer hot path (lsi.geometry.ldi.forward_splat, compose_layers=True,
-trg_downsampling=1: project + z-weight + bilinear forward splat + soft-z compose) over one batch of B synthetic
-LDIs already resident in HBM.  Rank 0 prints ONE JSON line.
+A "step" = one pass of the hot path over one batch of B synthetic source images already resident in HBM: the U-Net
+trunk + L heads predict the LDI (ldi_enc_dec.py:196-213), lsi.geometry.ldi.forward_splat renders it into the target
+camera (ldi_enc_dec.py:307-318, compose_layers=True).  Rank 0 prints ONE JSON line.
 """
 import argparse
 import ctypes
@@ -31,9 +32,9 @@ import torch
 H, W, L, B_PER_GPU = 256, 832, 4, 64
 MAX_DISP, BG_DISP, ZBUF_SCALE, DS = 0.4, 1e-3, 50.0, 1.0      # kitti constants, ldi_enc_dec.py:421-425
 METRIC = 'rendered views/sec at 256x832x4-layer'
-WORKLOAD = ('KITTI-like 256x832, 4-layer LDI, batch %d per GPU: lsi.geometry.ldi.forward_splat '
-            '(compose_layers=True, trg_downsampling=1); renderer slice only -- the encoder-decoder CNN is not yet in '
-            'the step' % B_PER_GPU)
+WORKLOAD = ('KITTI-like 256x832 image -> encoder-decoder U-Net + 4 LDI heads (W zero-padded to 896 for the U-Net, '
+            'prediction cropped; TF32 tcgen05 convs, batch-stat BN) -> forward_splat(compose_layers=True, '
+            'trg_downsampling=1) -> rendered target view; batch %d per GPU' % B_PER_GPU)
 
 
 def bytes_fwd_per_view(has_mask):
@@ -104,29 +105,48 @@ def make_inputs(batch, seed):
     return out
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's own CPU algorithm (TF-1.4 is not installable here, so this is the op-for-op
-    CPU restatement oracle/lsi_oracle.py, `kind: port`) on the host cores, bounded sample of the same workload."""
-    if rank != 0:
-        return
+def _oracle_view_fn(views):
+    """The reference CPU path for `views` views: oracle CNN (lsi_oracle_nets) + oracle renderer (lsi_oracle), same
+    padding policy as the B200 path."""
     from oracle import lsi_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    views = 2                                    # bounded sample: 2 of the 64 views per step
+    from oracle import lsi_oracle_nets as N
+    rs = np.random.RandomState(0)
+    img = torch.tensor(rs.uniform(0, 1, (views, H, W, 3)).astype(np.float32))
+    wp = -(-W // 128) * 128
+    padded = torch.zeros(views, H, wp, 3)
+    padded[:, :, :W] = img
+    params = N.init_params(L, seed=0)
     s = make_inputs(views, 0)
-    ldi = tuple(torch.tensor(s[k]) for k in ('tex', 'mask', 'disp'))
     cam = [torch.tensor(s[k]) for k in ('k_s', 'k_t', 'rot', 't')]
     pc = O.pixel_coords(views, H, W)
     kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+
+    def fn():
+        with torch.no_grad():
+            tex, masks, disps = N.predict_ldi(params, padded, L, MAX_DISP)
+            ldi = (tex[:, :, :, :W].contiguous(), masks[:, :, :, :W].contiguous(), disps[:, :, :, :W].contiguous())
+            return O.forward_splat(ldi, pc, *cam, **kw)
+    return fn
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU algorithm (TF-1.4 is not installable here, so this is the op-for-op
+    CPU restatement under oracle/, `kind: port`) on the host cores, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    views = 2                                    # bounded sample: 2 of the 64 views per step
+    fn = _oracle_view_fn(views)
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     for _ in range(warm):
-        O.forward_splat(ldi, pc, *cam, **kw)
+        fn()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.forward_splat(ldi, pc, *cam, **kw)
+        fn()
     dt = (time.perf_counter() - t0) / steps
     v = views / dt
-    sample = '%d of %d views per step, %d steps, torch CPU %d threads' % (views, B_PER_GPU, steps, cores)
+    sample = '%d of %d views per step, %d steps, torch CPU %d threads (oracle CNN + oracle renderer)' % (views, B_PER_GPU, steps, cores)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'views/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -136,31 +156,26 @@ def run_reference(args, rank):
 
 
 def cpu_baseline():
-    from oracle import lsi_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     views = 2
-    s = make_inputs(views, 0)
-    ldi = tuple(torch.tensor(s[k]) for k in ('tex', 'mask', 'disp'))
-    cam = [torch.tensor(s[k]) for k in ('k_s', 'k_t', 'rot', 't')]
-    pc = O.pixel_coords(views, H, W)
-    kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
-    O.forward_splat(ldi, pc, *cam, **kw)
+    fn = _oracle_view_fn(views)
+    fn()
     reps, t0 = 0, time.perf_counter()
-    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
-        O.forward_splat(ldi, pc, *cam, **kw)
+    while reps < 2 or (time.perf_counter() - t0 < 12.0 and reps < 20):
+        fn()
         reps += 1
     dt = (time.perf_counter() - t0) / reps
     return {'value': views / dt, 'unit': 'views/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d of %d views x %d reps of oracle/lsi_oracle.forward_splat (reference decomposition: per layer 3 '
-                      'splats, per channel x 4 corners scatter-into-zeros + add), torch CPU fp32' % (views, B_PER_GPU, reps)}
+            'sample': '%d of %d views x %d reps of the oracle (lsi_oracle_nets.predict_ldi + lsi_oracle.forward_splat in the '
+                      'reference decomposition), torch CPU fp32' % (views, B_PER_GPU, reps)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -181,22 +196,28 @@ def main():
 
     from lsi import _b200
     from lsi.geometry import ldi as ldi_utils
-    from lsi.nnutils import helpers
+    from lsi.nnutils import helpers, nets, train_utils
     lib = _b200.lib()
 
     B = B_PER_GPU
     host = make_inputs(B, seed=rank)
-    has_mask = False                               # nets.py:205: masks are all ones on the training path
-    tex, disp = torch.tensor(host['tex'], device=dev), torch.tensor(host['disp'], device=dev)
-    masks = torch.ones(L, B, H, W, 1, device=dev)
-    masks._lsi_all_ones = True
+    rs = np.random.RandomState(100 + rank)
+    from oracle import gen_inputs
+    img_host = np.stack([gen_inputs.band_limited(rs, (H, W), 3) for _ in range(8)] * (B // 8)).astype(np.float32)
+    imgs = torch.tensor(img_host, device=dev)
     cam = [torch.tensor(host[k], device=dev) for k in ('k_s', 'k_t', 'rot', 't')]
     pc = helpers.pixel_coords(B, H, W, device=dev)
+    opts = train_utils.default_opts(dataset='kitti', n_layers=L, batch_size=B, img_height=H, img_width=W,
+                                    zbuf_scale=ZBUF_SCALE)
+    store = nets.ParamStore(device=dev, seed=0)           # random-init weights of the reference architecture
     kw = dict(compose_layers=True, trg_downsampling=DS, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
+    with torch.no_grad():
+        train_utils.predict_ldi(imgs[:1], opts, store, reuse=False)      # creates the variables
 
-    def step():
+    def step(x=None):
         with torch.no_grad():
-            return ldi_utils.forward_splat((tex, masks, disp), pc, *cam, **kw)
+            ldi = train_utils.predict_ldi(imgs if x is None else x, opts, store, reuse=True)
+            return ldi_utils.forward_splat(tuple(ldi), pc, *cam, **kw)
 
     def barrier():
         if dist is not None:
@@ -225,38 +246,63 @@ def main():
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    # --- roofline of the dominant kernel (forward splat), timed live with CUDA events on its stream -------------
+    # --- per-kernel timing (CUDA events on the launching stream, live) -------------------------------------------
     lib.lsi_b200_kernel_timing_enable(1)
     for _ in range(args.steps):
         step()
     torch.cuda.synchronize()
-    kms, kn = (ctypes.c_double * 4)(), (ctypes.c_int * 4)()
+    kms, kn = (ctypes.c_double * 8)(), (ctypes.c_int * 8)()
     _b200.call('lsi_b200_kernel_timing_collect', ctypes.cast(kms, ctypes.c_void_p), ctypes.cast(kn, ctypes.c_void_p))
     lib.lsi_b200_kernel_timing_enable(0)
     peak, peak_src = load_peaks()
-    n_src, n_trg = H * W, int(H * DS) * int(W * DS)
-    splat_bytes_per_step = 4.0 * (5 if has_mask else 4) * L * n_src * B      # the splat kernel's algorithmic reads
-    splat_ms_per_step = kms[0] / args.steps
-    norm_ms_per_step = kms[1] / args.steps
-    achieved = splat_bytes_per_step / (splat_ms_per_step * 1e-3) / 1e9
-    step_bytes = bytes_fwd_per_view(has_mask) * B
-    roofline = {'bound': 'hbm', 'kernel': 'splat_fwd (forward splat; launches per step: %d)' % (kn[0] // args.steps),
+    n_src = H * W
+    splat_bytes_per_step = 4.0 * 4 * L * n_src * B          # packed (r,g,b,disp) head output read once by the splat kernel
+    splat_ms = kms[0] / args.steps
+    achieved = splat_bytes_per_step / (splat_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'splat_fwd_fast_kernel (forward splat; %d launches per step)' % (kn[0] // args.steps),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
-                'traffic': None, 'algorithmic_bytes_per_step': splat_bytes_per_step,
-                'kernel_ms_per_step': splat_ms_per_step, 'normalize_ms_per_step': norm_ms_per_step,
-                'step_achieved_gbs': step_bytes / (ms_per_step * 1e-3) / 1e9,
-                'step_frac': step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+                'traffic': None, 'algorithmic_bytes_per_step': splat_bytes_per_step, 'kernel_ms_per_step': splat_ms,
+                'normalize_ms_per_step': kms[1] / args.steps}
+    wp = -(-W // 128) * 128
+    conv_flops = (21.8e9 + 23.0e9 * L) * (H * wp) / (256.0 * 768.0) * B      # forward 2*MAC per step
+    conv_ms = (kms[4] + kms[5]) / args.steps
+    conv = {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 TF32) + fp32 stem', 'achieved': conv_flops / (conv_ms * 1e-3) / 1e12,
+            'unit': 'TFLOP/s', 'kernel_ms_per_step': conv_ms, 'tc_ms_per_step': kms[4] / args.steps,
+            'fp32_ms_per_step': kms[5] / args.steps, 'flops_per_step': conv_flops,
+            'share_of_step': conv_ms / ms_per_step, 'note': 'TF32 dense peak is ~half of the measured bf16 peak in MEASURED_PEAKS.json'}
 
-    # --- end to end through the C ABI with HOST buffers: H2D of the LDI + cameras, render, D2H of img + wts --------
-    pin = {k: torch.tensor(host[k]).pin_memory() for k in ('tex', 'disp', 'k_s', 'k_t', 'rot', 't')}
+    # --- renderer slice alone (the kernel the roofline is about), LDIs resident in HBM ------------------------------
+    with torch.no_grad():
+        ldi_fixed = [t.contiguous() for t in train_utils.predict_ldi(imgs, opts, store, reuse=True)]
+    ldi_fixed[1]._lsi_all_ones = True
+    for _ in range(3):
+        ldi_utils.forward_splat(tuple(ldi_fixed), pc, *cam, **kw)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(20):
+        with torch.no_grad():
+            ldi_utils.forward_splat(tuple(ldi_fixed), pc, *cam, **kw)
+    r1.record()
+    torch.cuda.synchronize()
+    renderer_only = B / (r0.elapsed_time(r1) / 20 * 1e-3)
+    del ldi_fixed
+
+    # --- end to end through the public API with HOST buffers: H2D of images + cameras, CNN, render, D2H of the views --
+    pin_img = torch.tensor(img_host).pin_memory()
+    pin_cam = [torch.tensor(host[k]).pin_memory() for k in ('k_s', 'k_t', 'rot', 't')]
     out_img = torch.empty(1, B, int(H * DS), int(W * DS), 3).pin_memory()
     out_wts = torch.empty(1, B, int(H * DS), int(W * DS), 1).pin_memory()
-    desc = _b200.SplatDesc(L, B, H, W, int(H * DS), int(W * DS), DS, BG_DISP, MAX_DISP, ZBUF_SCALE, 1, 0, 3, 1, 1, 0)
-    hp = lambda t: ctypes.c_void_p(t.data_ptr())
 
     def e2e_step():
-        _b200.call('lsi_b200_forward_splat_host', desc, hp(pin['tex']), None, hp(pin['disp']), hp(pin['k_s']),
-                   hp(pin['k_t']), hp(pin['rot']), hp(pin['t']), hp(out_img), hp(out_wts), None)
+        with torch.no_grad():
+            x = pin_img.to(dev, non_blocking=True)
+            c = [t.to(dev, non_blocking=True) for t in pin_cam]
+            ldi = train_utils.predict_ldi(x, opts, store, reuse=True)
+            img, wts = ldi_utils.forward_splat(tuple(ldi), pc, *c, **kw)
+            out_img.copy_(img, non_blocking=True)
+            out_wts.copy_(wts, non_blocking=True)
+        torch.cuda.synchronize()
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -271,21 +317,23 @@ def main():
         tt = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = tt.item()
-    h2d = sum(pin[k].numel() * 4 for k in pin)
+    h2d = pin_img.numel() * 4 + sum(t.numel() * 4 for t in pin_cam)
     d2h = (out_img.numel() + out_wts.numel()) * 4
     e2e = {'value': world * B / e2e_s, 'unit': 'views/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-           'ms_per_step': e2e_s * 1e3, 'api': 'lsi_b200_forward_splat_host (pinned host buffers)'}
+           'ms_per_step': e2e_s * 1e3, 'api': 'lsi.nnutils.train_utils.predict_ldi + lsi.geometry.ldi.forward_splat on pinned host '
+                                              'images/cameras, rendered views copied back'}
 
     cpu = cpu_baseline() if (rank == 0 and world == 1) else None
     if rank == 0:
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'views/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'tf32 convs (fp32 accumulate) + f32 renderer', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'h': H, 'w': W, 'layers': L, 'batch_per_gpu': B, 'global_batch': world * B,
-                       'parallelism': 'dp%d (independent views per rank, no data-path collective)' % world,
-                       'l2_policy': 'inputs (%.2f GB per step) exceed the 126 MB L2' % (splat_bytes_per_step / 1e9)},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}))
+                       'parallelism': 'dp%d (independent views per rank, no data-path collective at inference)' % world,
+                       'l2_policy': 'per-step activations (several GB) exceed the 126 MB L2'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'conv': conv,
+            'renderer_only_views_per_s': renderer_only, 'cpu_baseline': cpu}))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -44,8 +44,9 @@ LSI_B200_API unsigned long long lsi_b200_launch_count(void);
 
 /* Measurement aid (bench.py's roofline): when enabled, CUDA events on the launching stream bracket every launch
  * of the renderer kernels.  collect() waits for them and returns, per kernel kind (0 = forward splat,
- * 1 = normalise/compose, 2 = backward target stage, 3 = backward source stage), the summed milliseconds and the
- * launch count since the last collect.  Arrays of 4. */
+ * 1 = normalise/compose, 2 = backward target stage, 3 = backward source stage, 4 = tcgen05 conv, 5 = fp32 conv,
+ * 6 = weight gradient, 7 = reserved), the summed milliseconds and the launch count since the last collect.
+ * Arrays of 8. */
 LSI_B200_API int lsi_b200_kernel_timing_enable(int on);
 LSI_B200_API int lsi_b200_kernel_timing_collect(double* ms_by_kind, int* launches_by_kind);
 

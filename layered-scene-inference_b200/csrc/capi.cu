@@ -1,6 +1,7 @@
 // C-ABI plumbing shared by every entry point: version, thread-local error text, launch counter.
 #include <atomic>
 #include <string.h>
+#include <vector>
 
 #include "capi_common.h"
 
@@ -18,8 +19,44 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+struct TimedLaunch { cudaEvent_t a, b; int kind; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+ScopedTiming::ScopedTiming(int k, cudaStream_t s) : st(s), kind(k), on(g_timing) {
+  if (on) { a = get_event(); b = get_event(); cudaEventRecord(a, st); }
+}
+ScopedTiming::~ScopedTiming() {
+  if (on) { cudaEventRecord(b, st); g_timed.push_back(TimedLaunch{a, b, kind}); }
+}
+
 }  // namespace lsi
 
 extern "C" int lsi_b200_version(void) { return 100; }
 extern "C" const char* lsi_b200_last_error(void) { return lsi::g_err; }
 extern "C" unsigned long long lsi_b200_launch_count(void) { return lsi::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int lsi_b200_kernel_timing_enable(int on) {
+  lsi::g_timing = on != 0;
+  return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_kernel_timing_collect(double* ms_by_kind, int* launches_by_kind) {
+  LSI_REQUIRE(ms_by_kind && launches_by_kind, "NULL pointer argument");
+  for (int k = 0; k < lsi::kNumKinds; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; }
+  for (const lsi::TimedLaunch& t : lsi::g_timed) {
+    LSI_CUDA(cudaEventSynchronize(t.b));
+    float ms = 0.f;
+    LSI_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+    ms_by_kind[t.kind] += ms; launches_by_kind[t.kind] += 1;
+    lsi::g_event_pool.push_back(t.a); lsi::g_event_pool.push_back(t.b);
+  }
+  lsi::g_timed.clear();
+  return LSI_B200_OK;
+}

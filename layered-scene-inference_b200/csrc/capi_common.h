@@ -15,6 +15,15 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Optional per-kernel timing for bench.py's roofline: CUDA events on the launching stream around a launch.
+enum KernelKind { kSplatFwd = 0, kNormalize = 1, kBwdTarget = 2, kBwdSource = 3, kConvTc = 4, kConvFp32 = 5, kWgrad = 6,
+                  kNnOther = 7, kNumKinds = 8 };
+struct ScopedTiming {
+  cudaStream_t st; cudaEvent_t a, b; int kind; bool on;
+  ScopedTiming(int kind, cudaStream_t s);
+  ~ScopedTiming();
+};
+
 }  // namespace lsi
 
 #define LSI_REQUIRE(cond, ...)              \

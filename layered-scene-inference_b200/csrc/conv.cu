@@ -260,12 +260,15 @@ extern "C" int lsi_b200_conv2d(const lsi_b200_conv_desc* d, const float* in, con
   p.Hp = d->h_out / s; p.Wp = d->w_out / s;
   const long long M = (long long)p.N * p.Hp * p.Wp;
   const unsigned gm = (unsigned)((M + kBM - 1) / kBM);
-  if (d->c_out > 32) {
-    dim3 grid(gm, (d->c_out + 63) / 64, s * s);
-    conv_gather_kernel<64, 4><<<grid, 256, 0, as_stream(stream)>>>(p);
-  } else {
-    dim3 grid(gm, 1, s * s);
-    conv_gather_kernel<32, 2><<<grid, 256, 0, as_stream(stream)>>>(p);
+  {
+    ScopedTiming tm(kConvFp32, as_stream(stream));
+    if (d->c_out > 32) {
+      dim3 grid(gm, (d->c_out + 63) / 64, s * s);
+      conv_gather_kernel<64, 4><<<grid, 256, 0, as_stream(stream)>>>(p);
+    } else {
+      dim3 grid(gm, 1, s * s);
+      conv_gather_kernel<32, 2><<<grid, 256, 0, as_stream(stream)>>>(p);
+    }
   }
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
@@ -297,7 +300,10 @@ extern "C" int lsi_b200_conv2d_wgrad(const lsi_b200_conv_desc* d, const float* b
   p.pix_per_split = (int)pps;
   if (!d->accumulate) LSI_CUDA(cudaMemsetAsync(dw, 0, (size_t)taps * p.Ca * p.Cb * sizeof(float), as_stream(stream)));
   dim3 grid(tiles, taps, (unsigned)splits);
-  conv_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  {
+    ScopedTiming tm(kWgrad, as_stream(stream));
+    conv_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  }
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }

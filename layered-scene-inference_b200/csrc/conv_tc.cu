@@ -356,7 +356,10 @@ extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a
     smem_set = smem;
   }
   dim3 grid((unsigned)(p.tiles_x * p.tiles_y * d->batch), (unsigned)(p.n_pad / p.n_tile), (unsigned)(s * s));
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
+  {
+    ScopedTiming tm(kConvTc, st);
+    conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
+  }
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }

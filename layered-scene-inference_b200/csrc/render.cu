@@ -6,8 +6,6 @@
 //   splat_fwd_*_kernel      one thread per (layer, source pixel): registers only, then vector reductions
 //                           (red.global.add.v4.f32) into acc4[b][q] = (sum w*omega*rgb, sum w*omega)
 //   normalize_kernel        acc4 (+ per-layer (sum w, sum w*d)) -> trg_img, trg_wts, trg_disp   (ldi.py:165-173)
-#include <vector>
-
 #include "capi_common.h"
 #include "common.cuh"
 #include "render_fast.cuh"
@@ -367,48 +365,9 @@ static float bg_weight(const lsi_b200_splat_desc* d) {
 template <typename K, typename P>
 static void launch3(K kern, dim3 grid, dim3 block, cudaStream_t st, const P& p) { kern<<<grid, block, 0, st>>>(p); }
 
-// Optional per-kernel timing for bench.py's roofline: CUDA events on the launching stream around each launch.
-enum KernelKind { kSplatFwd = 0, kNormalize = 1, kBwdTarget = 2, kBwdSource = 3, kNumKinds = 4 };
-struct TimedLaunch { cudaEvent_t a, b; int kind; };
-static bool g_timing = false;
-static std::vector<TimedLaunch> g_timed;
-static std::vector<cudaEvent_t> g_event_pool;
-
-static cudaEvent_t get_event() {
-  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
-  cudaEvent_t e; cudaEventCreate(&e); return e;
-}
-
-struct ScopedTiming {
-  cudaStream_t st; TimedLaunch t; bool on;
-  ScopedTiming(int kind, cudaStream_t s) : st(s), on(g_timing) {
-    if (on) { t.a = get_event(); t.b = get_event(); t.kind = kind; cudaEventRecord(t.a, st); }
-  }
-  ~ScopedTiming() { if (on) { cudaEventRecord(t.b, st); g_timed.push_back(t); } }
-};
-
 }  // namespace lsi
 
 using namespace lsi;
-
-extern "C" int lsi_b200_kernel_timing_enable(int on) {
-  g_timing = on != 0;
-  return LSI_B200_OK;
-}
-
-extern "C" int lsi_b200_kernel_timing_collect(double* ms_by_kind, int* launches_by_kind) {
-  LSI_REQUIRE(ms_by_kind && launches_by_kind, "NULL pointer argument");
-  for (int k = 0; k < kNumKinds; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; }
-  for (const TimedLaunch& t : g_timed) {
-    LSI_CUDA(cudaEventSynchronize(t.b));
-    float ms = 0.f;
-    LSI_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
-    ms_by_kind[t.kind] += ms; launches_by_kind[t.kind] += 1;
-    g_event_pool.push_back(t.a); g_event_pool.push_back(t.b);
-  }
-  g_timed.clear();
-  return LSI_B200_OK;
-}
 
 extern "C" int lsi_b200_projection_matrix(const float* k_s, const float* k_t, const float* rot, const float* t,
                                           int batch, int inverse, float* out, void* stream) {

@@ -194,10 +194,13 @@ def _wgrad(desc_kw, big, small, dw):
 class _Geometry(object):
     """Descriptors of one layer: forward, data gradient, weight gradient."""
 
-    def __init__(self, transposed, B, Hi, Wi, Cin, Cout, k, s):
+    def __init__(self, transposed, B, Hi, Wi, Cin, Cout, k, s, out_hw=None):
         self.transposed, self.B, self.Hi, self.Wi, self.Cin, self.Cout, self.k, self.s = transposed, B, Hi, Wi, Cin, Cout, k, s
         if not transposed:
             self.Ho, self.Wo = -(-Hi // s), -(-Wi // s)
+            if out_hw is not None:      # stride-1 conv evaluated on the top-left out_hw window only (crop fused into the conv)
+                assert s == 1 and out_hw[0] <= self.Ho and out_hw[1] <= self.Wo
+                self.Ho, self.Wo = out_hw
             pt, pl = same_pad(Hi, k, s)[0], same_pad(Wi, k, s)[0]
             if s > 1 and (Hi % s or Wi % s):
                 raise ValueError('stride-%d conv needs even input sizes, got %dx%d' % (s, Hi, Wi))
@@ -355,7 +358,7 @@ def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False,
 
 
 def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=None, reuse=False, is_training=True,
-                        _scope='pixelwise_pred', _store=None):
+                        _scope='pixelwise_pred', _store=None, _out_hw=None):
     """nets.py:117-161 -- per layer its own decoder_simple, then a 3x3 conv + bias + sigmoid.  Returns
     (preds [L,B,H,W,nc], end_points)."""
     _require_training(is_training)
@@ -366,7 +369,7 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
         feat_l, _ = decoder_simple(feat, nconv=n_layerwise_steps, skip_feat=skip_feat, reuse=reuse, is_training=is_training,
                                    _scope=base + '/decoder', _store=store)
         B, H, W, cin = feat_l.shape
-        geo = _Geometry(False, B, H, W, cin, nc, 3, 1)
+        geo = _Geometry(False, B, H, W, cin, nc, 3, 1, out_hw=_out_hw)
         w = store.get('%s/pred_%d/weights' % (base, l), geo.w_shape, reuse, 'weights')
         b = store.get('%s/pred_%d/biases' % (base, l), [nc], reuse, 'biases')
         preds.append(_ConvBiasSigmoid.apply(feat_l, w, b, geo))
@@ -374,13 +377,14 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
 
 
 def ldi_predictor(feat, n_layers=1, reuse=False, n_layerwise_steps=0, skip_feat=None, pred_masks=False, is_training=True,
-                  _store=None):
+                  _store=None, _out_hw=None):
     """nets.py:164-208.  Returns ldi = [textures [L,B,H,W,3], masks [L,B,H,W,1], disps [L,B,H,W,1]].  The textures and
     disparities are channel views of the packed [L,B,H,W,nc] head output (no copy); with pred_masks=False the masks
     are all ones and tagged so (the renderer and the losses then never read them)."""
     nc = 3 + 1 + (1 if pred_masks else 0)
     pred, _ = pixelwise_predictor(feat, nc=nc, n_layers=n_layers, n_layerwise_steps=n_layerwise_steps, skip_feat=skip_feat,
-                                  reuse=reuse, is_training=is_training, _scope='ldi_tex_disp/pixelwise_pred', _store=_store)
+                                  reuse=reuse, is_training=is_training, _scope='ldi_tex_disp/pixelwise_pred', _store=_store,
+                                  _out_hw=_out_hw)
     if pred_masks:
         tex, masks, disps = pred[..., 0:3], pred[..., 3:4], pred[..., 4:5]
         masks = nn_helpers.enforce_bg_occupied(torch.sigmoid(masks))      # sigmoid applied twice, as nets.py:143,202
