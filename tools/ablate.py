@@ -27,7 +27,7 @@ for ds in (1.0, 0.5):
         lib.lsi_b200_kernel_timing_enable(1)
         for _ in range(10): step()
         torch.cuda.synchronize()
-        kms, kn = (ctypes.c_double * 4)(), (ctypes.c_int * 4)()
+        kms, kn = (ctypes.c_double * 8)(), (ctypes.c_int * 8)()
         _b200.call('lsi_b200_kernel_timing_collect', ctypes.cast(kms, ctypes.c_void_p), ctypes.cast(kn, ctypes.c_void_p))
         lib.lsi_b200_kernel_timing_enable(0)
         gb = 4.0 * 4 * bench.L * bench.H * bench.W * B / 1e9
