@@ -64,7 +64,8 @@ typedef struct lsi_b200_splat_desc {
    * separate tex/disp/mask tensors, 4/4 when tex and disp are views into the packed [L,B,H,W,4] head
    * output (nets.py:204).  (layer,batch) images must be densely packed: image stride = h_s*w_s*px_stride. */
   int tex_px_stride, disp_px_stride, mask_px_stride;
-  int variant;                                 /* 0 = default; 1 = plain global-atomic kernel (ablation)   */
+  int variant;                                 /* 0 = default; 1 = plain global-atomic kernel (ablation);   */
+                                               /* 2 = deterministic row-owner kernel for rectified poses     */
 } lsi_b200_splat_desc;
 
 /* src->trg (inverse==0, projection.py:71-86) or trg->src (inverse!=0, projection.py:89-106) 4x4 matrices.

@@ -9,6 +9,7 @@
 #include "capi_common.h"
 #include "common.cuh"
 #include "render_fast.cuh"
+#include "render_rowowner.cuh"
 
 namespace lsi {
 
@@ -27,7 +28,7 @@ __device__ void inv3x3(const double* a, double* o) {
 
 __global__ void proj_matrix_kernel(const float* __restrict__ k_s, const float* __restrict__ k_t,
                                    const float* __restrict__ rot, const float* __restrict__ t, int batch, int inverse,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, int* __restrict__ rect_flags) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   double ks[9], kt[9], r[9], tr[3], kinv[9], rt[9], tt[3];
@@ -57,6 +58,9 @@ __global__ void proj_matrix_kernel(const float* __restrict__ k_s, const float* _
     o[i * 4 + 3] = (float)col[i];
   }
   o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+  // rectified pose class (row-owner kernel): n == 1, y' independent of x and d, rows keep their order
+  if (rect_flags)
+    rect_flags[b] = (o[8] == 0.f && o[9] == 0.f && o[10] == 1.f && o[11] == 0.f && o[4] == 0.f && o[7] == 0.f && o[5] > 0.f) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -117,17 +121,30 @@ __global__ void __launch_bounds__(256) splat_fwd_atomic_kernel(const FwdParams p
 // ldi.py:165-173: per-layer disparity normalisation, compose (sum, sum, max), image normalisation.
 // bg canvases (ldi.py:115-125) are folded in here: every layer canvas starts at bg_wt for img and wts.
 // ---------------------------------------------------------------------------------------------------------
+// zero the chunk accumulators of the images the reduction kernels will render (skips row-owner images)
+__global__ void __launch_bounds__(256) zero_acc_kernel(float4* __restrict__ acc4, int nl_acc, int bc, int n_trg, int b0,
+                                                       const int* __restrict__ skip) {
+  const int bl = blockIdx.y;
+  if (skip && skip[b0 + bl]) return;
+  for (int l = 0; l < nl_acc; ++l) {
+    float4* a = acc4 + ((size_t)l * bc + bl) * n_trg;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_trg; i += gridDim.x * blockDim.x) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 struct NormParams {
   const float4* acc4; const float2* accd;
   float* img; float* wts; float* disp;
   int L, B, b0, bc, n_trg, compose, accd_b, accd_b0;
   float bg_wt;
+  const int* skip;
 };
 
 __global__ void __launch_bounds__(256) normalize_kernel(const NormParams p) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= p.n_trg) return;
   const int bl = blockIdx.y, b = p.b0 + bl;
+  if (p.skip && p.skip[b]) return;
   const int lo = blockIdx.z;   // output layer (0 when composing)
   const float4 a = p.acc4[((size_t)lo * p.bc + bl) * p.n_trg + q];
   const float nb = p.compose ? (float)p.L * p.bg_wt : p.bg_wt;
@@ -287,6 +304,15 @@ __global__ void __launch_bounds__(256) splat_bwd_source_kernel(const BwdBParams 
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+static bool rowowner_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LSI_B200_ROWOWNER");   // measured slower than the reduction kernels: opt-in
+    on = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+
 static int chunk_budget_mb() {
   static int mb = -1;
   if (mb < 0) {
@@ -310,7 +336,7 @@ static FwdPlan plan_forward(const lsi_b200_splat_desc* d) {
   if (bc > 65535) bc = 65535;
   pl.bc = (int)bc;
   pl.off_mats = 0;
-  pl.off_acc4 = align_up((size_t)d->batch * 16 * sizeof(float), 256);
+  pl.off_acc4 = align_up((size_t)d->batch * 17 * sizeof(float), 256);   // matrices + rectified-class flags
   pl.off_accd = pl.off_acc4 + align_up(n_trg * 16 * pl.nl_acc * bc, 256);
   pl.total = pl.off_accd + (d->compute_trg_disp ? align_up(n_trg * 8 * d->n_layers * bc, 256) : 0);
   return pl;
@@ -373,7 +399,7 @@ extern "C" int lsi_b200_projection_matrix(const float* k_s, const float* k_t, co
                                           int batch, int inverse, float* out, void* stream) {
   LSI_REQUIRE(k_s && k_t && rot && t && out, "NULL pointer argument");
   LSI_REQUIRE(batch >= 1, "batch=%d must be >= 1", batch);
-  proj_matrix_kernel<<<(batch + 63) / 64, 64, 0, as_stream(stream)>>>(k_s, k_t, rot, t, batch, inverse ? 1 : 0, out);
+  proj_matrix_kernel<<<(batch + 63) / 64, 64, 0, as_stream(stream)>>>(k_s, k_t, rot, t, batch, inverse ? 1 : 0, out, nullptr);
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }
@@ -402,7 +428,8 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
   float* mats = reinterpret_cast<float*>(ws + pl.off_mats);
-  proj_matrix_kernel<<<(d->batch + 63) / 64, 64, 0, st>>>(k_s, k_t, rot, t, d->batch, 0, mats);
+  int* rect_flags = reinterpret_cast<int*>(mats + (size_t)d->batch * 16);
+  proj_matrix_kernel<<<(d->batch + 63) / 64, 64, 0, st>>>(k_s, k_t, rot, t, d->batch, 0, mats, rect_flags);
   LSI_LAUNCH_CHECK();
 
   const int n_src = d->h_s * d->w_s, n_trg = d->h_t * d->w_t;
@@ -415,9 +442,42 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   // fast path: standard grid, no focal shift, no trg_disp, 16-byte aligned rows, planar (3/1/1) or packed (4/4) layout
   const bool packed = d->tex_px_stride == 4 && d->disp_px_stride == 4 && disp == tex + 3;
   const bool planar = d->tex_px_stride == 3 && d->disp_px_stride == 1;
-  const bool fast = (d->variant == 0 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
+  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
                     (!mask || d->mask_px_stride == 1) && (!packed || ((uintptr_t)tex & 15) == 0) && d->h_s <= 65535 &&
                     bc_fits_grid;
+  // rectified-stereo pose class: warp-owned target rows in shared memory, written once (render_rowowner.cuh); images of
+  // any other class fall through to the reduction kernels below, which skip the flagged ones
+  const int* skip = nullptr;
+  const bool fast_eligible = fast;
+  if (fast_eligible && (d->variant == 2 || rowowner_enabled())) {
+    int R = (int)(14336 / ((size_t)d->w_t * 16));
+    if (R > 4) R = 4;
+    if (R > d->h_t) R = d->h_t;
+    if (R >= 1) {
+      RowOwnerParams r;
+      r.tex = tex; r.disp = disp; r.mask = mask; r.mats = mats; r.flags = rect_flags; r.img = trg_img; r.wts = trg_wts;
+      r.L = d->n_layers; r.B = d->batch; r.H = d->h_s; r.W = d->w_s; r.h_t = d->h_t; r.w_t = d->w_t; r.R = R;
+      r.bands = (d->h_t + R - 1) / R; r.compose = d->compose_layers ? 1 : 0;
+      r.ds = d->trg_downsampling; r.inv_max_disp = 1.f / d->max_disp;
+      r.k2 = d->zbuf_scale * 1.4426950408889634f; r.k2h = 0.5f * r.k2; r.bg_wt = bg_weight(d);
+      const size_t smem = (size_t)4 * R * d->w_t * 16;
+      static size_t smem_set[4] = {0, 0, 0, 0};
+      const int ki = (mask ? 2 : 0) | (packed ? 1 : 0);
+      auto kern = ki == 0 ? splat_rowowner_kernel<false, false> : ki == 1 ? splat_rowowner_kernel<false, true>
+                : ki == 2 ? splat_rowowner_kernel<true, false> : splat_rowowner_kernel<true, true>;
+      if (smem > smem_set[ki]) {
+        LSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[ki] = smem;
+      }
+      const long long tasks = (long long)d->batch * r.bands;
+      {
+        ScopedTiming tm(kSplatFwd, st);
+        kern<<<(unsigned)((tasks + 3) / 4), 128, smem, st>>>(r);
+      }
+      LSI_LAUNCH_CHECK();
+      skip = rect_flags;
+    }
+  }
   for (int b0 = 0; b0 < d->batch; b0 += pl.bc) {
     const int bc = (d->batch - b0 < pl.bc) ? d->batch - b0 : pl.bc;
     FwdParams p;
@@ -430,7 +490,12 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
     p.acc_per_layer = d->compose_layers ? 0 : 1;
     p.accd_b = own_accd ? bc : d->batch; p.accd_b0 = own_accd ? b0 : 0;
     p.gp = geom_of(d);
-    LSI_CUDA(cudaMemsetAsync(p.acc4, 0, (size_t)pl.nl_acc * bc * n_trg * 16, st));
+    if (skip) {
+      zero_acc_kernel<<<dim3(64, bc), 256, 0, st>>>(p.acc4, pl.nl_acc, bc, n_trg, b0, skip);
+      LSI_LAUNCH_CHECK();
+    } else {
+      LSI_CUDA(cudaMemsetAsync(p.acc4, 0, (size_t)pl.nl_acc * bc * n_trg * 16, st));
+    }
     if (own_accd) LSI_CUDA(cudaMemsetAsync(p.accd, 0, (size_t)d->n_layers * bc * n_trg * 8, st));
     if (fast) {
       FastParams f;
@@ -440,6 +505,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
       f.ds = d->trg_downsampling; f.inv_max_disp = 1.f / d->max_disp;
       f.k2 = d->zbuf_scale * 1.4426950408889634f; f.k2h = 0.5f * f.k2;
       f.ablate = (d->variant >= 100) ? d->variant - 100 : 0;
+      f.skip = skip;
       dim3 fgrid((d->w_s + 63) / 64, d->h_s, bc), fblock(64);
       {
         ScopedTiming tm(kSplatFwd, st);
@@ -456,6 +522,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
         NormFastParams nf;
         nf.acc4 = p.acc4; nf.img = trg_img; nf.wts = trg_wts; nf.B = d->batch; nf.b0 = b0; nf.bc = bc; nf.n_trg = n_trg;
         nf.nb = d->compose_layers ? (float)d->n_layers * bg_weight(d) : bg_weight(d);
+        nf.skip = skip;
         {
           ScopedTiming tm(kNormalize, st);
           normalize_fast_kernel<<<dim3((n_trg / 4 + 255) / 256, bc, pl.nl_acc), 256, 0, st>>>(nf);
@@ -484,7 +551,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
     NormParams np;
     np.acc4 = p.acc4; np.accd = p.accd; np.img = trg_img; np.wts = trg_wts; np.disp = has_disp ? trg_disp : nullptr;
     np.L = d->n_layers; np.B = d->batch; np.b0 = b0; np.bc = bc; np.n_trg = n_trg; np.compose = d->compose_layers ? 1 : 0;
-    np.accd_b = p.accd_b; np.accd_b0 = p.accd_b0; np.bg_wt = bg_weight(d);
+    np.accd_b = p.accd_b; np.accd_b0 = p.accd_b0; np.bg_wt = bg_weight(d); np.skip = skip;
     {
       ScopedTiming tm(kNormalize, st);
       normalize_kernel<<<dim3((n_trg + 255) / 256, bc, pl.nl_acc), 256, 0, st>>>(np);
@@ -513,7 +580,7 @@ extern "C" int lsi_b200_forward_splat_backward(const lsi_b200_splat_desc* d, con
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
   float* mats = reinterpret_cast<float*>(ws + pl.off_mats);
-  proj_matrix_kernel<<<(d->batch + 63) / 64, 64, 0, st>>>(k_s, k_t, rot, t, d->batch, 0, mats);
+  proj_matrix_kernel<<<(d->batch + 63) / 64, 64, 0, st>>>(k_s, k_t, rot, t, d->batch, 0, mats, nullptr);
   LSI_LAUNCH_CHECK();
   const int n_src = d->h_s * d->w_s, n_trg = d->h_t * d->w_t;
   for (int b0 = 0; b0 < d->batch; b0 += pl.bc) {

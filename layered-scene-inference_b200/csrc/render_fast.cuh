@@ -26,6 +26,7 @@ struct FastParams {
   float ds, inv_max_disp;
   float k2, k2h;            // zb = ex2(clip(r)*k2 - k2h), k2 = scale*log2(e), k2h = 0.5*k2
   int ablate;               // measurement only: 1 = no reductions issued, 2 = reductions to the pixel's own cell
+  const int* skip;          // per batch element: 1 = already rendered by the row-owner kernel (nullable)
 };
 
 struct AxisW {   // one axis of the bilinear footprint: integer base, the two weights (validity folded in)
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(64, 16) splat_fwd_fast_kernel(const FastParams
   const bool active = j < p.W;
   const int i = blockIdx.y;
   const int bl = blockIdx.z, b = p.b0 + bl;
+  if (p.skip && p.skip[b]) return;   // uniform per block
   const Mat34 M = load_mat(p.mats, b);
   // pose class (uniform per block): n == 1 for every (x, y, d)?  y independent of x and d?
   const bool affine = (M.m[8] == 0.f) && (M.m[9] == 0.f) && (M.m[10] == 1.f) && (M.m[11] == 0.f);
@@ -194,12 +196,14 @@ struct NormFastParams {
   const float4* acc4; float* img; float* wts;
   int B, b0, bc, n_trg;
   float nb;   // bg_wt * (number of canvases summed into one accumulator)
+  const int* skip;
 };
 
 __global__ void __launch_bounds__(256) normalize_fast_kernel(const NormFastParams p) {
   const int q4 = blockIdx.x * blockDim.x + threadIdx.x;
   if (q4 * 4 >= p.n_trg) return;
   const int bl = blockIdx.y, b = p.b0 + bl, lo = blockIdx.z;
+  if (p.skip && p.skip[b]) return;
   const float4* a = p.acc4 + ((size_t)lo * p.bc + bl) * p.n_trg + (size_t)q4 * 4;
   const size_t o = ((size_t)lo * p.B + b) * p.n_trg + (size_t)q4 * 4;
   float v[12], w[4];

@@ -90,6 +90,16 @@ def test_forward_splat_input_forms_agree(lsi_mods, name):
     alt = ldi.forward_splat((tex, mask, disp), pc, *cam, compute_trg_disp=True, _variant=1, **kw)
     for a, b in zip(ref, alt):
         assert rel_err(a.cpu(), b.cpu()) < 1e-5
+    # deterministic row-owner kernel (rectified poses; other poses fall through to the reduction kernels), both
+    # compose modes; run twice: bitwise reproducible
+    for compose in (True, False):
+        base = ldi.forward_splat((tex, mask, disp), pc, *cam, compose_layers=compose, **kw)
+        ro1 = ldi.forward_splat((tex, mask, disp), pc, *cam, compose_layers=compose, _variant=2, **kw)
+        ro2 = ldi.forward_splat((tex, mask, disp), pc, *cam, compose_layers=compose, _variant=2, **kw)
+        for a, b, c in zip(base, ro1, ro2):
+            assert rel_err(b.cpu(), a.cpu()) < 1e-5
+            if name.startswith('fs_kitti'):
+                assert torch.equal(b, c)
     ones = torch.ones_like(mask)
     a = ldi.forward_splat((tex, ones, disp), pc, *cam, **kw)
     ones._lsi_all_ones = True
