@@ -23,7 +23,7 @@ namespace lsi {
 
 constexpr int kTileH = 8, kTileW = 16, kTileM = kTileH * kTileW;   // 128 output pixels = 128 TMEM lanes
 constexpr int kKC = 32;                                            // fp32 channels per K chunk = one 128-byte row
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kThreads = 192;
 
 struct TcParams {
@@ -35,6 +35,9 @@ struct TcParams {
   int kh, kw, stride, pad_t, pad_l, mode;
   int n_tile, n_pad;          // UMMA N, padded Cout
   int epilogue, accumulate;
+  int batch, total_tiles;     // persistent tile loop
+  int stages;                 // smem ring depth (2..4): shallower rings let 2-3 CTAs share an SM so that one CTA's
+                              // prologue/epilogue overlaps another's main loop
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -88,7 +91,37 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int n_img, y0, x0, n0, py, px, ky0, kx0, nky, nkx;
+};
+
+// persistent tile index -> (phase, Cout tile, image, patch); phases and Cout tiles are the slow dimensions so that
+// concurrently running CTAs share the same weights
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile, int s) {
+  TileCoord c;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int spatial = per_img * p.batch;
+  const int n_tiles_n = p.n_pad / p.n_tile;
+  const int sp = tile % spatial; int rest = tile / spatial;
+  const int nt = rest % n_tiles_n; const int ph = rest / n_tiles_n;
+  c.n_img = sp / per_img;
+  const int r = sp - c.n_img * per_img;
+  c.y0 = (r / p.tiles_x) * kTileH; c.x0 = (r % p.tiles_x) * kTileW;
+  c.n0 = nt * p.n_tile;
+  c.py = (p.mode == 1) ? ph / s : 0; c.px = (p.mode == 1) ? ph % s : 0;
+  c.ky0 = (p.mode == 1) ? ((c.py + p.pad_t) % s) : 0; c.kx0 = (p.mode == 1) ? ((c.px + p.pad_l) % s) : 0;
+  c.nky = (p.kh - c.ky0 + s - 1) / s; c.nkx = (p.kw - c.kx0 + s - 1) / s;
+  return c;
+}
+
+// Persistent CTAs: each loops over output tiles.  The TMA producer runs ahead across tile boundaries through the
+// shared-memory ring; the MMA issuer alternates between two TMEM accumulator buffers so that the epilogue warps drain
+// tile i while tile i+1 is being accumulated (small-K layers -- 3x3x32 -- are prologue/epilogue bound otherwise).
+__global__ void __launch_bounds__(kThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -96,33 +129,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.n_tile * 128;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  const int kStages = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
-  uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tmem_full = empty + kMaxStages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = (p.mode == 1) ? p.stride : 1;
-  const int py = (p.mode == 1) ? (int)blockIdx.z / s : 0, px = (p.mode == 1) ? (int)blockIdx.z % s : 0;
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; const int n_img = t / p.tiles_y;
-  const int y0 = ty * kTileH, x0 = tx * kTileW;       // patch origin in phase space
-  const int n0 = blockIdx.y * p.n_tile;
-
-  const int ky0 = (p.mode == 1) ? ((py + p.pad_t) % s) : 0, kx0 = (p.mode == 1) ? ((px + p.pad_l) % s) : 0;
-  const int nky = (p.kh - ky0 + s - 1) / s, nkx = (p.kw - kx0 + s - 1) / s;
   const int chunks = (p.Ca + p.Cb) / kKC;
-  const int k_iters = nky * nkx * chunks;
 
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.n_tile) tmem_cols <<= 1;
+  uint32_t acc_cols = 32;                        // columns of one accumulator buffer
+  while ((int)acc_cols < p.n_tile) acc_cols <<= 1;
+  const uint32_t tmem_cols = acc_cols * 2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -137,21 +163,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      for (int it = 0; it < k_iters; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty[st], ph ^ 1);
-        const int tap = it / chunks, c0 = (it - tap * chunks) * kKC;
-        const int ky = ky0 + (tap / nkx) * s, kx = kx0 + (tap % nkx) * s;
-        int ys, xs;
-        if (p.mode == 0) { ys = y0 * p.stride - p.pad_t + ky; xs = x0 * p.stride - p.pad_l + kx; }
-        else { ys = y0 + (py + p.pad_t - ky) / s; xs = x0 + (px + p.pad_l - kx) / s; }   // exact: tap list matches the phase
-        uint8_t* sa = smem + st * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full[st], a_bytes + b_bytes);
-        if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs, ys, n_img);
-        else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs, ys, n_img);
-        tma_load_2d(sb, &map_w, &full[st], c0, (ky * p.kw + kx) * p.n_pad + n0);
+      int it = 0;                                // ring position, continues across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord c = tile_coord(p, tile, s);
+        const int k_iters = c.nky * c.nkx * chunks;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[st], ph ^ 1);
+          const int tap = k / chunks, c0 = (k - tap * chunks) * kKC;
+          const int ky = c.ky0 + (tap / c.nkx) * s, kx = c.kx0 + (tap % c.nkx) * s;
+          int ys, xs;
+          if (p.mode == 0) { ys = c.y0 * p.stride - p.pad_t + ky; xs = c.x0 * p.stride - p.pad_l + kx; }
+          else { ys = c.y0 + (c.py + p.pad_t - ky) / s; xs = c.x0 + (c.px + p.pad_l - kx) / s; }   // exact: tap list matches the phase
+          uint8_t* sa = smem + st * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full[st], a_bytes + b_bytes);
+          if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs, ys, c.n_img);
+          else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs, ys, c.n_img);
+          tma_load_2d(sb, &map_w, &full[st], c0, (ky * p.kw + kx) * p.n_pad + c.n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -159,74 +190,92 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ---------------- MMA issuer ----------------
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      for (int it = 0; it < k_iters; ++it) {
-        const int st = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full[st], ph);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const TileCoord c = tile_coord(p, tile, s);
+        const int k_iters = c.nky * c.nkx * chunks;
+        const int buf = tcount & 1;
+        mbar_wait(&tmem_empty[buf], ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + a_bytes;
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + a_bytes;
 #pragma unroll
-        for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
-          umma_tf32(tmem_base, umma_desc(sa + kk * 32), umma_desc(sb + kk * 32), idesc, (it | kk) != 0);
+          for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+            umma_tf32(tmem_d, umma_desc(sa + kk * 32), umma_desc(sb + kk * 32), idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty[st]);                 // frees the stage once these MMAs have read it
         }
-        umma_commit(&empty[st]);                 // frees the stage once these MMAs have read it
+        umma_commit(&tmem_full[buf]);              // accumulator complete
       }
-      umma_commit(tmem_full);                    // accumulator complete
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int lg = warp & 3;                     // TMEM lane group this warp may access
     const int row = lg * 32 + lane;              // = A tile row = pixel within the patch
     const int hy = row / kTileW, wx = row % kTileW;
-    int oy = y0 + hy, ox = x0 + wx;
-    const bool in_range = oy < p.Hp && ox < p.Wp;
-    if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
-    float* dst = p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + n0;
-    for (int c = 0; c < p.n_tile; c += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c;
-      if (p.n_tile - c >= 32) {
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-      } else {   // n_tile == 16
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr));
-      }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (in_range) {
-        const int nvalid = min(min(32, p.n_tile - c), p.Co - (n0 + c));
-        if (nvalid == 32 && p.epilogue == 0 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst + c) & 15) == 0)) {
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const TileCoord c = tile_coord(p, tile, s);
+      const int buf = tcount & 1;
+      mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int oy = c.y0 + hy, ox = c.x0 + wx;
+      const bool in_range = oy < p.Hp && ox < p.Wp;
+      if (p.mode == 1) { oy = oy * s + c.py; ox = ox * s + c.px; }
+      float* dst = p.out + ((size_t)(c.n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0;
+      for (int cc = 0; cc < p.n_tile; cc += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc;
+        if (p.n_tile - cc >= 32) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+        } else {   // n_tile == 16
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cc + 32 >= p.n_tile) {               // last read of this accumulator: hand the buffer back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (in_range) {
+          const int nvalid = min(min(32, p.n_tile - cc), p.Co - (c.n0 + cc));
+          if (nvalid == 32 && p.epilogue == 0 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst + cc) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        } else {
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + cc + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < nvalid) {
-              float v = __uint_as_float(r[j]);
-              if (p.epilogue >= 1) v += __ldg(p.bias + n0 + c + j);
-              if (p.epilogue == 2) v = 1.f / (1.f + expf(-v));
-              if (p.accumulate) v += dst[c + j];
-              dst[c + j] = v;
+            for (int j = 0; j < 32; ++j) {
+              if (j < nvalid) {
+                float v = __uint_as_float(r[j]);
+                if (p.epilogue >= 1) v += __ldg(p.bias + c.n0 + cc + j);
+                if (p.epilogue == 2) v = 1.f / (1.f + expf(-v));
+                if (p.accumulate) v += dst[cc + j];
+                dst[cc + j] = v;
+              }
             }
           }
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -243,6 +292,16 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
     const int tap = (int)(i / ((long long)cin * n_pad));
     wk[i] = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
   }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -349,13 +408,27 @@ extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
   const uint32_t b_bytes = ((uint32_t)p.n_tile * 128 + 1023) & ~1023u;
-  const size_t smem = (size_t)kStages * (kTileM * 128 + b_bytes) + 256 + 1024;
+  const uint32_t stage_bytes = kTileM * 128 + b_bytes;
+  int stages = (int)((74u * 1024u) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * d->batch), (unsigned)(p.n_pad / p.n_tile), (unsigned)(s * s));
+  p.batch = d->batch;
+  p.total_tiles = p.tiles_x * p.tiles_y * d->batch * (p.n_pad / p.n_tile) * s * s;
+  int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
+  const int tmem_per_cta = 2 * (p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256);
+  if (ctas_per_sm > 512 / tmem_per_cta) ctas_per_sm = 512 / tmem_per_cta;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  int n_ctas = num_sms() * ctas_per_sm;
+  if (n_ctas > p.total_tiles) n_ctas = p.total_tiles;
+  dim3 grid((unsigned)n_ctas);
   {
     ScopedTiming tm(kConvTc, st);
     conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
