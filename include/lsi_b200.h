@@ -196,13 +196,20 @@ LSI_B200_API int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in
                                     int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* lsi_b200_conv2d_tc that also reduces the batch-norm statistics of its output in the epilogue (per-CTA partial sums
+ * from the TMEM registers, then one finalise kernel): bn_stats[c] = (mean, rsqrt(biased var + eps)). */
+LSI_B200_API int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
+                                            int in_b_c_stride, const float* w, float* out, float* bn_stats, float bn_eps,
+                                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* slim.batch_norm(is_training=True, center=True, scale=False) + ReLU (nets.py:263-272): batch statistics over the
- * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward.  workspace:
+ * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward (stats_given != 0: they were
+ * already produced by lsi_b200_conv2d_tc_bnstats and only the normalise + ReLU pass runs).  workspace:
  * lsi_b200_bn_workspace_bytes(channels). */
 LSI_B200_API size_t lsi_b200_bn_workspace_bytes(int channels);
 LSI_B200_API int lsi_b200_bn_relu_forward(const float* x, const float* beta, float* y, float* stats, long long n_pixels,
                                           int channels, int x_c_stride, int y_c_stride, float eps, int relu,
-                                          void* workspace, void* stream);
+                                          int stats_given, void* workspace, void* stream);
 /* dx (and dbeta_sums[c] = (sum dz, sum dz*xhat); dbeta = the first) from dy, with dz = dy*[y>0] when relu. */
 LSI_B200_API int lsi_b200_bn_relu_backward(const float* x, const float* y, const float* dy, const float* stats, float* dx,
                                            float* dbeta_sums, long long n_pixels, int channels, int x_c_stride,

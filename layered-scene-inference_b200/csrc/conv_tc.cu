@@ -36,6 +36,7 @@ struct TcParams {
   int n_tile, n_pad;          // UMMA N, padded Cout
   int epilogue, accumulate;
   int batch, total_tiles;     // persistent tile loop
+  float* stat_part;           // [gridDim.x*4][n_pad][2] per-(CTA,warp) channel sums of the output (batch-norm statistics), or NULL
   int stages;                 // smem ring depth (2..4): shallower rings let 2-3 CTAs share an SM so that one CTA's
                               // prologue/epilogue overlaps another's main loop
 };
@@ -135,6 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = empty + kMaxStages;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_stage = reinterpret_cast<float*>(smem + kStages * stage_bytes + 256);   // [4 warps][32][33]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = (p.mode == 1) ? p.stride : 1;
@@ -218,10 +220,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int lg = warp & 3;                     // TMEM lane group this warp may access
     const int row = lg * 32 + lane;              // = A tile row = pixel within the patch
     const int hy = row / kTileW, wx = row % kTileW;
+    float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};   // channel (n0 + 32*i + lane) sums of this warp's pixels
+    int stat_n0 = -1;
+    float* stg = stat_stage + (size_t)lg * 32 * 33;
+    float* my_part = p.stat_part ? p.stat_part + ((size_t)blockIdx.x * 4 + lg) * p.n_pad * 2 : nullptr;
+    auto flush_stats = [&]() {
+      if (my_part && stat_n0 >= 0) {
+        for (int i = 0; i < 4; ++i) {
+          const int ch = stat_n0 + 32 * i + lane;
+          if (32 * i < p.n_tile && ch < p.n_pad && (32 * i + lane) < p.n_tile) { my_part[2 * ch] += ssum[i]; my_part[2 * ch + 1] += ssq[i]; }
+          ssum[i] = 0.f; ssq[i] = 0.f;
+        }
+      }
+    };
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       const TileCoord c = tile_coord(p, tile, s);
       const int buf = tcount & 1;
+      if (my_part && c.n0 != stat_n0) { flush_stats(); stat_n0 = c.n0; }
       mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int oy = c.y0 + hy, ox = c.x0 + wx;
@@ -252,6 +268,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty[buf]);
         }
+        if (my_part) {   // per-channel sum / sum of squares over this warp's 32 pixels, via a padded smem transpose
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = (in_range && j < p.n_tile - cc) ? __uint_as_float(r[j]) : 0.f;
+          __syncwarp();
+          float a = 0.f, b2 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) { const float v = stg[rr * 33 + lane]; a += v; b2 = fmaf(v, v, b2); }
+          ssum[cc >> 5] += a; ssq[cc >> 5] += b2;
+        }
         if (in_range) {
           const int nvalid = min(min(32, p.n_tile - cc), p.Co - (c.n0 + cc));
           if (nvalid == 32 && p.epilogue == 0 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst + cc) & 15) == 0)) {
@@ -274,6 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
+    flush_stats();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -323,10 +350,12 @@ static EncodeTiledFn get_encode() {
 
 using namespace lsi;
 
+static size_t stat_part_bytes(size_t n_pad) { return (size_t)148 * 4 * 4 * n_pad * 2 * sizeof(float) * 2; }   // generous: <= 4 CTAs/SM
+
 extern "C" size_t lsi_b200_conv2d_tc_workspace_bytes(const lsi_b200_conv_desc* d) {
   if (!d) return 0;
   const size_t n_pad = (size_t)(d->c_out + 15) / 16 * 16;
-  return (size_t)d->kh * d->kw * n_pad * (size_t)d->c_in * sizeof(float) + 256;
+  return (size_t)d->kh * d->kw * n_pad * (size_t)d->c_in * sizeof(float) + 512 + stat_part_bytes(n_pad);
 }
 
 extern "C" int lsi_b200_conv2d_tc_supported(const lsi_b200_conv_desc* d, int c_in_a) {
@@ -344,9 +373,45 @@ extern "C" int lsi_b200_conv2d_tc_supported(const lsi_b200_conv_desc* d, int c_i
 
 // Same contract as lsi_b200_conv2d, plus an optional second input source: channels [0, c_in_a) come from `in_a`
 // (pixel stride in_c_stride), channels [c_in_a, c_in) from `in_b` (pixel stride in_b_c_stride) -- tf.concat on the fly.
+namespace lsi {
+__global__ void __launch_bounds__(256) finalize_stats_f32_kernel(const float* __restrict__ partial, int nparts, int n_pad, int C,
+                                                                 long long P, float eps, float* __restrict__ out) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = lane; i < nparts; i += 32) { a += (double)partial[((size_t)i * n_pad + c) * 2]; b += (double)partial[((size_t)i * n_pad + c) * 2 + 1]; }
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane != 0) return;
+  const double mean = a / (double)P;
+  double var = b / (double)P - mean * mean;
+  if (var < 0.0) var = 0.0;
+  out[2 * c] = (float)mean; out[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+}  // namespace lsi
+
+static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b, int in_b_c_stride,
+                          const float* w, const float* bias, float* out, float* bn_stats, float bn_eps, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
                                   int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
                                   size_t workspace_bytes, void* stream) {
+  return conv2d_tc_impl(d, in_a, c_in_a, in_b, in_b_c_stride, w, bias, out, nullptr, 0.f, workspace, workspace_bytes, stream);
+}
+
+// conv + batch statistics of its output in one pass: bn_stats[c] = (mean, rsqrt(biased var + eps)) over all output pixels
+extern "C" int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
+                                          int in_b_c_stride, const float* w, float* out, float* bn_stats, float bn_eps,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  LSI_REQUIRE(bn_stats != nullptr, "NULL pointer argument");
+  LSI_REQUIRE(d && d->epilogue == 0 && d->accumulate == 0, "bn statistics need a plain conv output");
+  return conv2d_tc_impl(d, in_a, c_in_a, in_b, in_b_c_stride, w, nullptr, out, bn_stats, bn_eps, workspace, workspace_bytes, stream);
+}
+
+static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b, int in_b_c_stride,
+                          const float* w, const float* bias, float* out, float* bn_stats, float bn_eps, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   LSI_REQUIRE(d && in_a && w && out && workspace, "NULL pointer argument");
   LSI_REQUIRE(lsi_b200_conv2d_tc_supported(d, c_in_a), "shape not supported by the tensor-core path");
   LSI_REQUIRE(c_in_a == d->c_in || (in_b && in_b_c_stride % 4 == 0 && in_b_c_stride >= d->c_in - c_in_a), "bad second source");
@@ -413,7 +478,7 @@ extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + (bn_stats ? 4 * 32 * 33 * sizeof(float) : 0);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -429,10 +494,21 @@ extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a
   int n_ctas = num_sms() * ctas_per_sm;
   if (n_ctas > p.total_tiles) n_ctas = p.total_tiles;
   dim3 grid((unsigned)n_ctas);
+  p.stat_part = nullptr;
+  if (bn_stats) {
+    p.stat_part = wk + (size_t)taps * p.n_pad * d->c_in;
+    p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
+    LSI_CUDA(cudaMemsetAsync(p.stat_part, 0, (size_t)n_ctas * 4 * p.n_pad * 2 * sizeof(float), st));
+  }
   {
     ScopedTiming tm(kConvTc, st);
     conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
   }
   LSI_LAUNCH_CHECK();
+  if (bn_stats) {
+    finalize_stats_f32_kernel<<<(d->c_out + 7) / 8, 256, 0, st>>>(p.stat_part, n_ctas * 4, p.n_pad, d->c_out,
+                                                                 (long long)d->batch * d->h_out * d->w_out, bn_eps, bn_stats);
+    LSI_LAUNCH_CHECK();
+  }
   return LSI_B200_OK;
 }

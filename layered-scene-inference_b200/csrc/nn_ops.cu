@@ -199,17 +199,19 @@ static int stat_blocks(long long P) {
 }
 
 extern "C" int lsi_b200_bn_relu_forward(const float* x, const float* beta, float* y, float* stats, long long n_pixels,
-                                        int channels, int x_c_stride, int y_c_stride, float eps, int relu, void* workspace,
-                                        void* stream) {
+                                        int channels, int x_c_stride, int y_c_stride, float eps, int relu, int stats_given,
+                                        void* workspace, void* stream) {
   LSI_REQUIRE(x && beta && y && stats && workspace, "NULL pointer argument");
   LSI_REQUIRE(n_pixels >= 1 && channels >= 1 && x_c_stride >= channels && y_c_stride >= channels, "bad sizes");
   cudaStream_t st = as_stream(stream);
-  const int nb = stat_blocks(n_pixels);
-  StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
-  channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
-  LSI_LAUNCH_CHECK();
-  finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, eps, 0, stats);
-  LSI_LAUNCH_CHECK();
+  if (!stats_given) {   // otherwise `stats` was produced by the conv epilogue (lsi_b200_conv2d_tc_bnstats)
+    const int nb = stat_blocks(n_pixels);
+    StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
+    channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
+    LSI_LAUNCH_CHECK();
+    finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, eps, 0, stats);
+    LSI_LAUNCH_CHECK();
+  }
   BnApplyParams ap{x, stats, beta, y, n_pixels, channels, x_c_stride, y_c_stride, relu};
   if (x_c_stride == channels && y_c_stride == channels && channels % 4 == 0 && ((uintptr_t)x & 15) == 0 &&
       ((uintptr_t)y & 15) == 0 && ((uintptr_t)beta & 15) == 0)

@@ -174,16 +174,33 @@ def _tc_workspace(device, nbytes):
     return _tc_ws[key]
 
 
-def _conv(desc_kw, inp, w, out, bias=None):
+def _tc_ok(d, c_in_a, *tensors):
+    return (_CONV_MODE == 'tf32' and _b200.lib().lsi_b200_conv2d_tc_supported(d, c_in_a) == 1
+            and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
+
+
+def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=None):
+    """One convolution launch.  inp_b: optional second source (channels [c_in_a, c_in)), i.e. tf.concat on the fly
+    (tensor-core path only).  bn_stats: [C,2] tensor to receive (mean, rsqrt(var+eps)) of the output, reduced in the conv
+    epilogue (tensor-core path only).  Returns True when bn_stats was filled."""
     d = _b200.ConvDesc(**desc_kw)
     lib = _b200.lib()
-    if _CONV_MODE == 'tf32' and lib.lsi_b200_conv2d_tc_supported(d, d.c_in) == 1 and inp.data_ptr() % 16 == 0:
+    ca = d.c_in if c_in_a is None else c_in_a
+    if _tc_ok(d, ca, inp, inp_b):
         nws = int(lib.lsi_b200_conv2d_tc_workspace_bytes(d))
         ws = _tc_workspace(inp.device, nws)
-        _b200.call('lsi_b200_conv2d_tc', d, _b200.ptr(inp), d.c_in, None, 0, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out),
-                   _b200.ptr(ws), ws.numel(), _b200.stream())
-        return
+        cb_stride = 0 if inp_b is None else inp_b.shape[-1]
+        if bn_stats is not None and d.epilogue == 0 and d.accumulate == 0:
+            _b200.call('lsi_b200_conv2d_tc_bnstats', d, _b200.ptr(inp), ca, _b200.ptr(inp_b), cb_stride, _b200.ptr(w),
+                       _b200.ptr(out), _b200.ptr(bn_stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+            return True
+        _b200.call('lsi_b200_conv2d_tc', d, _b200.ptr(inp), ca, _b200.ptr(inp_b), cb_stride, _b200.ptr(w), _b200.ptr(bias),
+                   _b200.ptr(out), _b200.ptr(ws), ws.numel(), _b200.stream())
+        return False
+    if inp_b is not None:
+        raise RuntimeError('lsi_b200: two-source convolution needs the tensor-core path')
     _b200.call('lsi_b200_conv2d', d, _b200.ptr(inp), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out), _b200.stream())
+    return False
 
 
 def _wgrad(desc_kw, big, small, dw):
@@ -234,12 +251,13 @@ class _ConvBNReLU(torch.autograd.Function):
     def forward(ctx, x, w, beta, geo):
         dev = x.device
         z = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout, dtype=torch.float32, device=dev)
-        _conv(geo.fwd, x, w, z)
-        y = torch.empty_like(z)
         stats = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+        have_stats = _conv(geo.fwd, x, w, z, bn_stats=stats)        # tensor-core path reduces the BN statistics in its epilogue
+        y = torch.empty_like(z)
         P = geo.B * geo.Ho * geo.Wo
         _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(y), _b200.ptr(stats), P, geo.Cout,
-                   geo.Cout, geo.Cout, BN_EPS, 1, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+                   geo.Cout, geo.Cout, BN_EPS, 1, 1 if have_stats else 0, _b200.ptr(_bn_workspace(dev, geo.Cout)),
+                   _b200.stream())
         ctx.save_for_backward(x, w, z, y, stats)
         ctx.geo = geo
         return y
@@ -330,6 +348,26 @@ def ctypes_offset(t, n_floats):
 
 
 def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False):
+    """conv / up-conv + batch-stat BN + ReLU.  `x` may be a pair (a, b) standing for tf.concat([a, b], axis=3): under
+    no_grad the tensor-core kernel reads the two sources directly; with autograd the concat is materialised."""
+    if isinstance(x, (tuple, list)):
+        a, b = (_b200.dev_f32(t, scope + ' input') for t in x)
+        B, H, W, ca = a.shape
+        cin = ca + b.shape[3]
+        geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
+        w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+        beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+        d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=ca))
+        if not torch.is_grad_enabled() and _tc_ok(d, ca, a, b):
+            dev = a.device
+            z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float32, device=dev)
+            stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
+            have = _conv(dict(geo.fwd, in_c_stride=ca), a, w, z, bn_stats=stats, inp_b=b, c_in_a=ca)
+            _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(z), _b200.ptr(stats),
+                       B * geo.Ho * geo.Wo, cout, cout, cout, BN_EPS, 1, 1 if have else 0,
+                       _b200.ptr(_bn_workspace(dev, cout)), _b200.stream())      # in place: nothing is kept for a backward
+            return z
+        x = _ConcatChannels.apply(a, b)
     x = _b200.dev_f32(x, scope + ' input')
     B, H, W, cin = x.shape
     geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
@@ -351,7 +389,7 @@ def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False,
         n_filt = n_filters[nc - 1]
         feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True)
         if nc > 1 and skip_feat is not None:
-            feat = _ConcatChannels.apply(feat, skip_feat[-nc + 1])
+            feat = (feat, skip_feat[-nc + 1])                    # tf.concat([feat, skip], axis=3), nets.py:108-109
         feat = _conv_layer(store, '%s/upcnv%db' % (_scope, nc), feat, n_filt, 3, 1, reuse)
         end_points['%s/upcnv%db' % (_scope, nc)] = feat
     return feat, end_points
@@ -417,7 +455,7 @@ def encoder_decoder_unet(inp_img, nz=1000, is_training=True, reuse=False, nl_dif
     for k, cout, skip in DEC[:7 - nl_diff_enc_dec]:
         up = _conv_layer(store, '%s/upcnv%d' % (sc, k), feat, cout, 4, 2, reuse, transposed=True)
         if skip is not None:
-            up = _ConcatChannels.apply(up, ep[skip])
+            up = (up, ep[skip])                                  # tf.concat([upcnv, skip], axis=3), nets.py:300,...
         feat = _conv_layer(store, '%s/icnv%d' % (sc, k), up, cout, 3, 1, reuse)
         ep['icnv%d' % k] = feat
         feats_dec.append(feat)
