@@ -196,6 +196,12 @@ LSI_B200_API int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in
                                     int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* Tensor-core weight gradient (tcgen05, both operands MN-major straight from NHWC TMA boxes, split-K over pixels,
+ * fp32 reductions into dw); same contract as lsi_b200_conv2d_wgrad. */
+LSI_B200_API int lsi_b200_conv2d_wgrad_tc_supported(const lsi_b200_conv_desc* d);
+LSI_B200_API int lsi_b200_conv2d_wgrad_tc(const lsi_b200_conv_desc* d, const float* big, const float* small, float* dw,
+                                          void* stream);
+
 /* lsi_b200_conv2d_tc that also reduces the batch-norm statistics of its output in the epilogue (per-CTA partial sums
  * from the TMEM registers, then one finalise kernel): bn_stats[c] = (mean, rsqrt(biased var + eps)). */
 LSI_B200_API int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,

@@ -60,6 +60,8 @@ SIGNATURES = {
     'lsi_b200_decreasing_disp_loss_backward': (_I, [_P, _I, _LL, _P, _P, _P]),
     'lsi_b200_conv2d': (_I, [_CP, _P, _P, _P, _P, _P]),
     'lsi_b200_conv2d_wgrad': (_I, [_CP, _P, _P, _P, _P]),
+    'lsi_b200_conv2d_wgrad_tc_supported': (_I, [_CP]),
+    'lsi_b200_conv2d_wgrad_tc': (_I, [_CP, _P, _P, _P, _P]),
     'lsi_b200_conv2d_tc_supported': (_I, [_CP, _I]),
     'lsi_b200_conv2d_tc_workspace_bytes': (_SZ, [_CP]),
     'lsi_b200_conv2d_tc': (_I, [_CP, _P, _I, _P, _I, _P, _P, _P, _P, _SZ, _P]),

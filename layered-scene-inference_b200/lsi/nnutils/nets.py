@@ -205,6 +205,10 @@ def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=Non
 
 def _wgrad(desc_kw, big, small, dw):
     d = _b200.ConvDesc(**desc_kw)
+    if (_CONV_MODE == 'tf32' and _b200.lib().lsi_b200_conv2d_wgrad_tc_supported(d) == 1 and big.data_ptr() % 16 == 0
+            and small.data_ptr() % 16 == 0):
+        _b200.call('lsi_b200_conv2d_wgrad_tc', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
+        return
     _b200.call('lsi_b200_conv2d_wgrad', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
 
 

@@ -90,3 +90,37 @@ def test_upconv_phase_decomposed(B, H, W, Cin, Cout):
 def test_conv_stride2_element_strides(B, H, W, Cin, Cout, k):
     out, ref = _run_both(B, H, W, Cin, Cout, k, 2, 0, False)
     assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Ca,Cb,k,s', [
+    (1, 8, 16, 32, 32, 3, 1),        # one pixel tile, 9 taps -> 3 M tiles (last one partial)
+    (2, 16, 32, 64, 64, 3, 1),       # two B blocks
+    (1, 11, 21, 96, 64, 3, 1),       # ragged spatial size
+    (1, 8, 16, 32, 4, 3, 1),         # prediction conv: 4 output channels
+    (2, 8, 16, 192, 128, 3, 1),      # two N tiles
+    (1, 8, 16, 32, 32, 7, 1),
+    (2, 16, 32, 32, 64, 5, 2),       # stride-2 conv: element strides on the big side
+    (1, 16, 32, 64, 128, 3, 2),
+    (2, 8, 16, 32, 64, 4, 2),        # transposed conv: big = dout (2H x 2W, 32 ch), small = input (H x W, 64 ch)
+    (1, 8, 16, 40, 24, 3, 1),        # channel counts that are not multiples of 32
+])
+def test_wgrad_tensor_core(B, H, W, Ca, Cb, k, s):
+    """lsi_b200_conv2d_wgrad_tc against the fp32 weight-gradient kernel; sizes are those of the strided-gather side
+    (H x W, Ca channels) like the descriptor's *_in fields."""
+    from lsi import _b200
+    from lsi.nnutils.nets import same_pad
+    torch.manual_seed(Ca + Cb + k)
+    Ho, Wo = -(-H // s), -(-W // s)
+    pt, pl = (1, 1) if (k, s) == (4, 2) else (same_pad(H, k, s)[0], same_pad(W, k, s)[0])
+    big = torch.randn(B, H, W, Ca, device='cuda')
+    small = torch.randn(B, Ho, Wo, Cb, device='cuda')
+    d = _b200.ConvDesc(batch=B, h_in=H, w_in=W, c_in=Ca, h_out=Ho, w_out=Wo, c_out=Cb, kh=k, kw=k, stride=s, pad_top=pt,
+                       pad_left=pl, mode=0, w_tap_stride=0, w_ci_stride=0, w_co_stride=0, in_c_stride=Ca, out_c_stride=Cb,
+                       epilogue=0, accumulate=0)
+    ref = torch.empty(k, k, Ca, Cb, device='cuda')
+    out = torch.full((k, k, Ca, Cb), 7.0, device='cuda')
+    _b200.call('lsi_b200_conv2d_wgrad', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(ref), _b200.stream())
+    assert _b200.lib().lsi_b200_conv2d_wgrad_tc_supported(d) == 1
+    _b200.call('lsi_b200_conv2d_wgrad_tc', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(out), _b200.stream())
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
