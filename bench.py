@@ -323,6 +323,39 @@ def main():
            'ms_per_step': e2e_s * 1e3, 'api': 'lsi.nnutils.train_utils.predict_ldi + lsi.geometry.ldi.forward_splat on pinned host '
                                               'images/cameras, rendered views copied back'}
 
+    # --- training step at BASELINE config 4's per-GPU shard (batch 8 per GPU, 256x832, L=4): two towers, view-synthesis
+    #     loss, backward, ONE all-reduce of the flat gradient buffer (NCCL, when world > 1), fused Adam -------------------
+    del imgs, pin_img, out_img, out_wts
+    torch.cuda.empty_cache()
+    tb = 8
+    topts = train_utils.default_opts(dataset='kitti', n_layers=L, batch_size=tb, img_height=H, img_width=W)
+    trainer = train_utils.Trainer(topts, store=nets.ParamStore(device=dev, seed=0))
+    rs2 = np.random.RandomState(200 + rank)
+    tbatch = {'imgs_src': torch.tensor(img_host[:tb], device=dev),
+              'imgs_trg': torch.tensor(np.ascontiguousarray(img_host[tb:2 * tb]), device=dev),
+              'k_s': cam[0][:tb].contiguous(), 'k_t': cam[1][:tb].contiguous(), 'rot_mat': cam[2][:tb].contiguous(),
+              'trans_mat': cam[3][:tb].contiguous()}
+    for _ in range(2):
+        trainer.train_step(tbatch)
+    barrier()
+    t_steps = max(2, min(args.steps, 5))
+    te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    te0.record()
+    for _ in range(t_steps):
+        tloss, _ = trainer.train_step(tbatch)
+    te1.record()
+    barrier()
+    tms = te0.elapsed_time(te1) / t_steps
+    if dist is not None:
+        tt = torch.tensor([tms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tms = tt.item()
+    train = {'ms_per_step': tms, 'image_pairs_per_s': world * tb / (tms * 1e-3), 'batch_per_gpu': tb, 'steps': t_steps,
+             'loss': float(tloss), 'grad_allreduce_bytes': int(trainer.store.flat_grad.numel() * 4),
+             'what': 'ldi_enc_dec.py training step: 2 U-Net towers + %d heads, self-consistency + 4 forward splats + smoothness '
+                     '+ ordering losses, backward (tcgen05 dgrad/wgrad), %s, fused Adam' % (L, 'NCCL all-reduce of the flat '
+                     'gradient buffer' if world > 1 else 'no collective at 1 GPU')}
+
     cpu = cpu_baseline() if (rank == 0 and world == 1) else None
     if rank == 0:
         print(json.dumps({
@@ -333,7 +366,7 @@ def main():
                        'parallelism': 'dp%d (independent views per rank, no data-path collective at inference)' % world,
                        'l2_policy': 'per-step activations (several GB) exceed the 126 MB L2'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'conv': conv,
-            'renderer_only_views_per_s': renderer_only, 'cpu_baseline': cpu}))
+            'renderer_only_views_per_s': renderer_only, 'train': train, 'cpu_baseline': cpu}))
     if dist is not None:
         dist.destroy_process_group()
 
