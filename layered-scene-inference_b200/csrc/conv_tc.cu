@@ -36,6 +36,9 @@ struct TcParams {
   int n_tile, n_pad;          // UMMA N, padded Cout
   int epilogue, accumulate;
   int batch, total_tiles;     // persistent tile loop
+  int xm;                     // x-merge: 16x8 pixel tiles, ONE halo load per (ky, chunk) feeds all kx taps through shifted UMMA descriptors
+  int halo_w;                 // xm: pixels per halo row (tile width 8 + taps along x - 1, or padded to 16)
+  int th, tw;                 // tile height / width in pixels (8x16 default, 16x8 with xm)
   float* stat_part;           // [gridDim.x*4][n_pad][2] per-(CTA,warp) channel sums of the output (batch-norm statistics), or NULL
   int stages;                 // smem ring depth (2..4): shallower rings let 2-3 CTAs share an SM so that one CTA's
                               // prologue/epilogue overlaps another's main loop
@@ -80,6 +83,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
+// same, for a tile whose 8-row groups are `sbo` bytes apart and whose start address is shifted by whole 128-byte rows
+// (x-merged halo tiles).  Measured on B200: the tensor core derives the 128B-swizzle phase from the absolute shared-memory
+// address bits, exactly like TMA wrote it, so the base-offset field stays 0 (setting it to the row phase gives wrong
+// results) and SBO need not be a multiple of 1024 (1280 = a 10-pixel halo row works).
+__device__ __forceinline__ uint64_t umma_desc_shifted(uint32_t saddr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -111,7 +127,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile, int
   const int nt = rest % n_tiles_n; const int ph = rest / n_tiles_n;
   c.n_img = sp / per_img;
   const int r = sp - c.n_img * per_img;
-  c.y0 = (r / p.tiles_x) * kTileH; c.x0 = (r % p.tiles_x) * kTileW;
+  c.y0 = (r / p.tiles_x) * p.th; c.x0 = (r % p.tiles_x) * p.tw;
   c.n0 = nt * p.n_tile;
   c.py = (p.mode == 1) ? ph / s : 0; c.px = (p.mode == 1) ? ph % s : 0;
   c.ky0 = (p.mode == 1) ? ((c.py + p.pad_t) % s) : 0; c.kx0 = (p.mode == 1) ? ((c.px + p.pad_l) % s) : 0;
@@ -128,8 +144,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.n_tile * 128;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+  const uint32_t b_tap_bytes = ((uint32_t)p.n_tile * 128 + 1023) & ~1023u;
+  const uint32_t a_bytes = p.xm ? (uint32_t)p.halo_w * p.th * 128 : kTileM * 128;
+  const uint32_t b_bytes = (uint32_t)p.n_tile * 128;
+  const uint32_t stage_bytes = p.xm ? a_bytes + (uint32_t)p.kw * b_tap_bytes : a_bytes + b_tap_bytes;   // xm: up to kw weight tiles
   const int kStages = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   uint64_t* empty = full + kMaxStages;
@@ -168,18 +186,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int it = 0;                                // ring position, continues across tiles
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = tile_coord(p, tile, s);
-        const int k_iters = c.nky * c.nkx * chunks;
+        const int k_iters = p.xm ? c.nky * chunks : c.nky * c.nkx * chunks;
         for (int k = 0; k < k_iters; ++k, ++it) {
           const int st = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[st], ph ^ 1);
+          uint8_t* sa = smem + st * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          if (p.xm) {
+            // one halo tile (halo_w x th pixels) per (ky, chunk); tap j along x reads it shifted by off_j pixels
+            const int kyi = k / chunks, c0 = (k - kyi * chunks) * kKC;
+            const int ky = c.ky0 + kyi * s;
+            int ys, xs_min;
+            if (p.mode == 0) { ys = c.y0 - p.pad_t + ky; xs_min = c.x0 - p.pad_l; }
+            else { ys = c.y0 + (c.py + p.pad_t - ky) / s; xs_min = c.x0 + (c.px + p.pad_l - (c.kx0 + (c.nkx - 1) * s)) / s; }
+            mbar_expect_tx(&full[st], a_bytes + (uint32_t)c.nkx * b_bytes);
+            if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs_min, ys, c.n_img);
+            else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs_min, ys, c.n_img);
+            for (int j = 0; j < c.nkx; ++j) {
+              const int kx = c.kx0 + j * s;
+              tma_load_2d(sb + j * b_tap_bytes, &map_w, &full[st], c0, (ky * p.kw + kx) * p.n_pad + c.n0);
+            }
+            continue;
+          }
           const int tap = k / chunks, c0 = (k - tap * chunks) * kKC;
           const int ky = c.ky0 + (tap / c.nkx) * s, kx = c.kx0 + (tap % c.nkx) * s;
           int ys, xs;
           if (p.mode == 0) { ys = c.y0 * p.stride - p.pad_t + ky; xs = c.x0 * p.stride - p.pad_l + kx; }
           else { ys = c.y0 + (c.py + p.pad_t - ky) / s; xs = c.x0 + (c.px + p.pad_l - kx) / s; }   // exact: tap list matches the phase
-          uint8_t* sa = smem + st * stage_bytes;
-          uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full[st], a_bytes + b_bytes);
           if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs, ys, c.n_img);
           else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs, ys, c.n_img);
@@ -195,7 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const TileCoord c = tile_coord(p, tile, s);
-        const int k_iters = c.nky * c.nkx * chunks;
+        const int k_iters = p.xm ? c.nky * chunks : c.nky * c.nkx * chunks;
         const int buf = tcount & 1;
         mbar_wait(&tmem_empty[buf], ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -206,9 +240,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + a_bytes;
+          if (p.xm) {
+            for (int j = 0; j < c.nkx; ++j) {
+              const uint32_t off = (p.mode == 0) ? (uint32_t)j : (uint32_t)(c.nkx - 1 - j);   // pixels into the halo row
 #pragma unroll
-          for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
-            umma_tf32(tmem_d, umma_desc(sa + kk * 32), umma_desc(sb + kk * 32), idesc, (k | kk) != 0);
+              for (int kk = 0; kk < kKC / 8; ++kk)
+                umma_tf32(tmem_d, umma_desc_shifted(sa + off * 128 + kk * 32, (uint32_t)p.halo_w * 128),
+                          umma_desc(sb + j * b_tap_bytes + kk * 32), idesc, (k | j | kk) != 0);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+              umma_tf32(tmem_d, umma_desc(sa + kk * 32), umma_desc(sb + kk * 32), idesc, (k | kk) != 0);
+            }
           }
           umma_commit(&empty[st]);                 // frees the stage once these MMAs have read it
         }
@@ -219,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     const int lg = warp & 3;                     // TMEM lane group this warp may access
     const int row = lg * 32 + lane;              // = A tile row = pixel within the patch
-    const int hy = row / kTileW, wx = row % kTileW;
+    const int hy = row / p.tw, wx = row % p.tw;
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};   // channel (n0 + 32*i + lane) sums of this warp's pixels
     int stat_n0 = -1;
     float* stg = stat_stage + (size_t)lg * 32 * 33;
@@ -319,6 +363,17 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
     const int tap = (int)(i / ((long long)cin * n_pad));
     wk[i] = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
   }
+}
+
+static bool xmerge_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("LSI_B200_CONV_XMERGE"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1;
+}
+static bool xmerge_tight() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("LSI_B200_CONV_XMERGE_TIGHT"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1;
 }
 
 static int num_sms() {
@@ -426,7 +481,12 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
   p.out = out; p.bias = bias; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
   const int s = d->mode == 1 ? d->stride : 1;
   p.Hp = d->h_out / s; p.Wp = d->w_out / s;
-  p.tiles_x = (p.Wp + kTileW - 1) / kTileW; p.tiles_y = (p.Hp + kTileH - 1) / kTileH;
+  // x-merge: unit-stride gathers with more than one tap along x, on images wide enough for 16x8 tiles to make sense
+  const int nkx_max = (d->mode == 1) ? (d->kw + s - 1) / s : d->kw;
+  p.xm = (xmerge_enabled() && (d->mode == 1 || d->stride == 1) && nkx_max >= 2 && nkx_max <= 9 && p.Hp >= 16 && p.n_pad <= 128) ? 1 : 0;
+  p.th = p.xm ? 16 : kTileH; p.tw = p.xm ? 8 : kTileW;
+  p.halo_w = p.xm ? (xmerge_tight() ? p.tw + nkx_max - 1 : 16) : 0;
+  p.tiles_x = (p.Wp + p.tw - 1) / p.tw; p.tiles_y = (p.Hp + p.th - 1) / p.th;
   p.Ca = c_in_a; p.Cb = d->c_in - c_in_a;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
   p.n_pad = (d->c_out + 15) / 16 * 16;
@@ -452,6 +512,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
     cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
     cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)d->w_in * cs * 4, (cuuint64_t)d->h_in * d->w_in * cs * 4};
     cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((kTileW - 1) * es + 1), (cuuint32_t)((kTileH - 1) * es + 1), 1};
+    if (p.xm) { box[1] = (cuuint32_t)p.halo_w; box[2] = (cuuint32_t)p.th; }
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
     CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -473,7 +534,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
   const uint32_t b_bytes = ((uint32_t)p.n_tile * 128 + 1023) & ~1023u;
-  const uint32_t stage_bytes = kTileM * 128 + b_bytes;
+  const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * 128 + (uint32_t)d->kw * b_bytes : kTileM * 128 + b_bytes;
   int stages = (int)((74u * 1024u) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;

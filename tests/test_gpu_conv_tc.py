@@ -80,7 +80,23 @@ def test_conv_concat_on_the_fly_bias_sigmoid_accumulate():
     assert rel_err(out.cpu(), ref.cpu()) < TOL
 
 
-@pytest.mark.parametrize('B,H,W,Cin,Cout', [(1, 4, 8, 128, 64), (2, 8, 16, 64, 32), (1, 5, 9, 128, 128)])
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k', [
+    (1, 32, 24, 32, 32, 3),       # x-merged halo path (output height >= 16): one 10-pixel halo row per ky feeds 3 taps
+    (2, 21, 37, 96, 64, 3),       # ragged: partial 16x8 tiles
+    (1, 16, 16, 192, 128, 3),     # 6 channel chunks, N = 128
+    (1, 32, 16, 32, 4, 3),        # N padded to 16
+    (1, 16, 40, 32, 32, 7),       # 7 taps per halo row (14-pixel halo)
+    (1, 48, 16, 64, 64, 5),
+])
+def test_conv_stride1_xmerge(B, H, W, Cin, Cout, k):
+    out, ref = _run_both(B, H, W, Cin, Cout, k, 1, 0, False)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+    out, ref = _run_both(B, H, W, Cin, Cout, k, 1, 0, False, split=(32 if Cin >= 64 else None))
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(1, 4, 8, 128, 64), (2, 8, 16, 64, 32), (1, 5, 9, 128, 128), (1, 16, 24, 64, 32),
+                                            (2, 19, 11, 128, 64)])
 def test_upconv_phase_decomposed(B, H, W, Cin, Cout):
     out, ref = _run_both(B, H, W, Cin, Cout, 4, 2, 1, True)
     assert rel_err(out.cpu(), ref.cpu()) < TOL
