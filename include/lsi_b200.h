@@ -208,6 +208,21 @@ LSI_B200_API int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const f
                                             int in_b_c_stride, const float* w, float* out, float* bn_stats, float bn_eps,
                                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Halo-tile tensor-core convolution for the full-resolution few-channel layers of the LDI heads (nets.py:87-114: upcnv1
+ * 4x4/2 up-conv 64->32, upcnv1b 3x3 32->32; nets.py:137-159: pred 3x3 32->4 + bias + sigmoid): unit-stride gathers
+ * (mode 0 stride 1, or mode 1), c_in in {32,64,96,128}, c_out in {32,64} or <= 4 with out_c_stride 4.  The filter bank
+ * stays resident in shared memory and each 16x8 output tile reads ONE TMA halo box per 32-channel chunk.
+ * in_bn_stats/in_bn_beta (both or neither): the input is the RAW output of a slim.conv2d whose batch_norm + ReLU
+ * (nets.py:263-272) has not been applied yet -- (mean, rstd)[c_in] and beta[c_in]; it is applied on load, in shared
+ * memory, so the normalised tensor never exists in HBM.  out_bn_stats (optional, plain c_out in {32,64} convs): receives
+ * (mean, rsqrt(biased var + eps)) of this layer's raw output, reduced in the epilogue. */
+LSI_B200_API int lsi_b200_conv2d_halo_supported(const lsi_b200_conv_desc* d);
+LSI_B200_API size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc* d);
+LSI_B200_API int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats,
+                                      const float* in_bn_beta, const float* w, const float* bias, float* out,
+                                      float* out_bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* slim.batch_norm(is_training=True, center=True, scale=False) + ReLU (nets.py:263-272): batch statistics over the
  * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward (stats_given != 0: they were
  * already produced by lsi_b200_conv2d_tc_bnstats and only the normalise + ReLU pass runs).  workspace:

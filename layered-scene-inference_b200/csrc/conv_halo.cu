@@ -1,0 +1,615 @@
+// Halo-tile tensor-core convolution for the full-resolution, few-channel layers of the LDI heads (nets.py:87-114,
+// 137-159: upcnv1 64->32 4x4/2 up-conv, upcnv1b 32->32 3x3, pred 32->4 3x3 + bias + sigmoid).  These layers are
+// HBM-bound by arithmetic intensity (<= 40 flop/B), so the kernel is organised around bytes, not flops:
+//
+//   weights      the CTA's whole filter bank ([tap][N][Cin] K-major, <= 36 KB) is TMA-loaded ONCE and stays resident in
+//                shared memory; an up-conv CTA serves a single output phase (blockIdx % 4), i.e. 4 of the 16 taps.
+//   activations  ONE 4-D TMA box per (tile, 32-channel chunk): the (16 + kh - 1) x (8 + kw - 1) pixel halo of a 16 x 8
+//                output tile.  Every tap (ky, kx) is an MMA whose A descriptor starts (ky * halo_w + kx) 128-byte rows
+//                into that box (8-row groups halo_w rows apart): the tensor core applies the 128B swizzle on absolute
+//                shared-memory address bits, exactly as TMA wrote it, so shifted starts need no data movement.  L2->SM
+//                traffic per tile drops from 3 x 20 KB activations + 36 KB weights (x-merged kernel) to 23 KB.
+//   BN on load   the producing layer's batch-norm + ReLU (slim.batch_norm, nets.py:263-272) is applied to the halo tile
+//                IN shared memory by four transform warps (y = max(x * rstd + (beta - mean * rstd), 0); out-of-image
+//                pixels stay zero = SAME padding of the normalised tensor), so the normalised activation never
+//                exists in HBM: the separate bn_apply pass (read + write of every activation) disappears.
+//   epilogue     TMEM -> registers -> per-warp shared-memory staging -> (a) per-channel sum / sum-of-squares for this
+//                layer's own batch statistics, (b) 512-byte coalesced global stores (4 pixels x 128 B per instruction).
+//   pipeline     persistent CTAs; warp 0 TMA producer, warp 1 single-thread MMA issuer (double-buffered TMEM
+//                accumulators), warps 2-5 epilogue, warps 6-9 transform; mbarrier ring over tiles.
+#include <cuda.h>
+
+#include "capi_common.h"
+#include "common.cuh"
+
+namespace lsi {
+namespace {
+
+constexpr int kTH = 16, kTW = 8, kTileM = kTH * kTW;   // 128 output pixels = 128 TMEM lanes
+constexpr int kKC = 32;                                // fp32 channels per 128-byte row
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 320;
+constexpr int kStgPitch = 36;                          // floats per staged pixel (144 B: conflict-free 128-bit rows)
+constexpr int kMaxCin = 128;
+
+struct HaloParams {
+  float* out; const float* bias;
+  const float* in_stats; const float* in_beta;   // producer's (mean, rstd)[Cin] and beta[Cin]; NULL = input is final
+  float* stat_part;                              // [gridDim.x * 4][n_tile][2] channel sums of the output, or NULL
+  int Hin, Win, Ho, Wo, Co, out_cs, Hp, Wp;
+  int tiles_x, per_img, spatial_tiles;
+  int chunks, kh, kw, stride, pad_t, pad_l, mode;
+  int n_tile, epilogue, stages;
+  int halo_w, halo_h;
+  uint32_t halo_bytes, b_tap_bytes, w_bytes, div_halo_w;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major 128B-swizzled operand: 8-row groups `sbo` bytes apart, start address possibly shifted by whole 128-byte rows
+__device__ __forceinline__ uint64_t umma_desc_hi(uint32_t sbo) {
+  return ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint64_t hi, uint32_t saddr) { return hi | (uint64_t)((saddr >> 4) & 0x3FFF); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// true for exactly one lane of a converged warp; unlike `lane == 0` it tells ptxas that a single thread runs the
+// guarded region, so tcgen05/TMA operands go to uniform registers without a per-lane waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "@P1 mov.s32 %0, 1;\n"
+      "}\n" : "+r"(pred));
+  return pred != 0;
+}
+
+// ring position that advances without integer division
+struct Ring {
+  int st; uint32_t ph; int n;
+  __device__ __forceinline__ explicit Ring(int stages) : st(0), ph(0), n(stages) {}
+  __device__ __forceinline__ void next() { if (++st == n) { st = 0; ph ^= 1; } }
+};
+
+// (image, tile row, tile column) of the persistent tile sequence t0, t0 + step, ... advanced without integer division
+struct TileIter {
+  int n, ty, tx;             // current tile
+  int dn, dty, dtx;          // step decomposed in (images, tile rows, tile columns)
+  int tiles_x, tiles_y;
+  __device__ __forceinline__ TileIter(int t0, int step, int tiles_x_, int per_img) : tiles_x(tiles_x_), tiles_y(per_img / tiles_x_) {
+    n = t0 / per_img; int r = t0 - n * per_img; ty = r / tiles_x; tx = r - ty * tiles_x;
+    dn = step / per_img; r = step - dn * per_img; dty = r / tiles_x; dtx = r - dty * tiles_x;
+  }
+  __device__ __forceinline__ void next() {
+    tx += dtx; ty += dty; n += dn;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+  }
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
+  // carve: [resident weights][stages x chunks x halo tile][barriers 256 B][bn scale/shift 2 x 512 B][staging 4 x 32 x 36 floats]
+  const uint32_t stage_bytes = (uint32_t)p.chunks * p.halo_bytes;
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + p.w_bytes;
+  uint8_t* s_ctl = s_a + (size_t)p.stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_ctl);
+  uint64_t* xready = full + kMaxStages;
+  uint64_t* empty = xready + kMaxStages;
+  uint64_t* tmem_full = empty + kMaxStages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* wfull = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* bn_a = reinterpret_cast<float*>(s_ctl + 256);
+  float* bn_b = bn_a + kMaxCin;
+  float* staging = bn_b + kMaxCin;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool bn_in = p.in_stats != nullptr;
+
+  // phase of this CTA (up-conv / data-gradient mode: one of stride^2 output phases; plain conv: the only one)
+  const int s = (p.mode == 1) ? p.stride : 1;
+  const int G = s * s;
+  const int phase = (int)(blockIdx.x % G);
+  const int cta_in_group = (int)(blockIdx.x / G), ctas_per_group = (int)(gridDim.x / G);
+  const int py = phase / s, px = phase % s;
+  const int ky0 = (p.mode == 1) ? ((py + p.pad_t) % s) : 0, kx0 = (p.mode == 1) ? ((px + p.pad_l) % s) : 0;
+  const int nky = (p.kh - ky0 + s - 1) / s, nkx = (p.kw - kx0 + s - 1) / s;
+  // halo origin relative to the tile origin, in source pixels (exact divisions: the tap list matches the phase)
+  const int oy_off = (p.mode == 0) ? -p.pad_t : (py + p.pad_t - (ky0 + (nky - 1) * s)) / s;
+  const int ox_off = (p.mode == 0) ? -p.pad_l : (px + p.pad_l - (kx0 + (nkx - 1) * s)) / s;
+
+  const uint32_t acc_cols = p.n_tile <= 32 ? 32u : (p.n_tile <= 64 ? 64u : 128u);
+  const uint32_t tmem_cols = acc_cols * 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&xready[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (bn_in) {   // y = max(x * a + b, 0) with a = rstd, b = beta - mean * rstd
+    for (int c = threadIdx.x; c < p.chunks * kKC; c += kThreads) {
+      const float mean = __ldg(p.in_stats + 2 * c), rstd = __ldg(p.in_stats + 2 * c + 1);
+      bn_a[c] = rstd; bn_b[c] = fmaf(-mean, rstd, __ldg(p.in_beta + c));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- TMA producer ----------------
+      mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)p.n_tile * 128u);
+      for (int i = 0; i < nky; ++i)
+        for (int j = 0; j < nkx; ++j)
+          for (int ch = 0; ch < p.chunks; ++ch)
+            tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
+                        ((ky0 + i * s) * p.kw + (kx0 + j * s)) * p.n_tile);
+      Ring r(p.stages);
+      const uint32_t tx = (uint32_t)p.chunks * (uint32_t)(p.halo_w * p.halo_h) * 128u;
+      TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
+      for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, r.next(), ti.next()) {
+        const int n_img = ti.n, y0 = ti.ty * kTH, x0 = ti.tx * kTW;
+        mbar_wait(&empty[r.st], r.ph ^ 1);
+        mbar_expect_tx(&full[r.st], tx);
+        const uint32_t sa = smem_u32(s_a) + (uint32_t)r.st * stage_bytes;
+        for (int ch = 0; ch < p.chunks; ++ch)
+          tma_load_4d(sa + (uint32_t)ch * p.halo_bytes, &map_a, &full[r.st], ch * kKC, x0 + ox_off, y0 + oy_off, n_img);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- MMA issuer ----------------
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint64_t hi_a = umma_desc_hi((uint32_t)p.halo_w * 128u), hi_b = umma_desc_hi(1024u);
+      mbar_wait(wfull, 0);
+      const uint64_t b_desc0 = umma_desc(hi_b, smem_u32(s_w));
+      Ring r(p.stages);
+      int tcount = 0;
+      for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, r.next(), ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(&tmem_empty[buf], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        mbar_wait(bn_in ? &xready[r.st] : &full[r.st], r.ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
+        // descriptors advance by adding byte offsets >> 4 to the start-address field (no carry out of its 14 bits:
+        // every operand lives below 256 KB)
+        const uint64_t a_desc0 = umma_desc(hi_a, smem_u32(s_a) + (uint32_t)r.st * stage_bytes);
+        uint32_t acc = 0;
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          for (int i = 0; i < nky; ++i) {
+            const int dy = (p.mode == 0) ? i : nky - 1 - i;
+            for (int j = 0; j < nkx; ++j) {
+              const int dx = (p.mode == 0) ? j : nkx - 1 - j;
+              const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)ch * p.halo_bytes + (uint32_t)(dy * p.halo_w + dx) * 128u) >> 4);
+              const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+                umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                acc = 1;
+              }
+            }
+          }
+        }
+        umma_commit(&empty[r.st]);                 // frees the stage once these MMAs have read it
+        umma_commit(&tmem_full[buf]);              // accumulator complete
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- epilogue: TMEM -> registers -> staging -> global ----------------
+    const int lg = warp & 3;                     // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;              // A-tile row = pixel within the 16 x 8 patch
+    const int hy = row >> 3, wx = row & 7;
+    float* stg = staging + (size_t)lg * 32 * kStgPitch;
+    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};   // channel (32 * i + lane) sums over this warp's pixels
+    const bool direct4 = (p.Co <= 4 && p.out_cs == 4);   // prediction head: one 16-byte store per pixel
+    int tcount = 0;
+    TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
+    for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ++tcount, ti.next()) {
+      const int n_img = ti.n, y0 = ti.ty * kTH, x0 = ti.tx * kTW;
+      const int buf = tcount & 1;
+      mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool in_range = (y0 + hy) < p.Hp && (x0 + wx) < p.Wp;
+      for (int cc = 0; cc < p.n_tile; cc += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc;
+        if (p.n_tile - cc >= 32) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+        } else {   // n_tile == 16
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr));
+#pragma unroll
+          for (int j = 16; j < 32; ++j) r[j] = 0u;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cc + 32 >= p.n_tile) {               // last read of this accumulator: hand the buffer back to the MMA issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (direct4) {
+          if (in_range) {
+            int oy = y0 + hy, ox = x0 + wx;
+            if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[j] = __uint_as_float(r[j]);
+              if (p.epilogue >= 1 && j < p.Co) v[j] += __ldg(p.bias + j);
+              if (p.epilogue == 2) v[j] = 1.f / (1.f + expf(-v[j]));
+            }
+            float* dst = p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * 4;
+            if (p.Co == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (j < p.Co) dst[j] = v[j];
+            }
+          }
+          continue;
+        }
+        // stage this warp's 32 pixels x 32 channels (zero rows for pixels outside the output)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (p.epilogue >= 1) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + j));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          }
+          if (!in_range) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = v;
+        }
+        __syncwarp();
+        if (p.stat_part) {
+          float a = 0.f, b2 = 0.f;
+#pragma unroll 8
+          for (int q = 0; q < 32; ++q) { const float v = stg[q * kStgPitch + lane]; a += v; b2 = fmaf(v, v, b2); }
+          ssum[cc >> 5] += a; ssq[cc >> 5] += b2;
+        }
+        // coalesced stores: each instruction writes 4 pixels x 128 bytes
+        const int q4 = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pxi = i * 4 + q4;
+          int oy = y0 + lg * 4 + (pxi >> 3), ox = x0 + (pxi & 7);
+          if (oy < p.Hp && ox < p.Wp) {
+            if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
+            const float4 v = *reinterpret_cast<const float4*>(stg + pxi * kStgPitch + c4);
+            *reinterpret_cast<float4*>(p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4) = v;
+          }
+        }
+      }
+    }
+    if (p.stat_part) {
+      float* my_part = p.stat_part + ((size_t)blockIdx.x * 4 + lg) * p.n_tile * 2;
+      for (int i = 0; i < 2; ++i) {
+        const int ch = 32 * i + lane;
+        if (ch < p.n_tile) { my_part[2 * ch] = ssum[i]; my_part[2 * ch + 1] = ssq[i]; }
+      }
+    }
+  } else if (bn_in) {
+    // ---------------- transform: producer's batch-norm + ReLU applied to the halo tile in shared memory ----------------
+    // thread -> (16-byte column j, pixels p0, p0+16, ...): (p0 + 16k) & 7 == p0 & 7, so the 128B-swizzle phase, hence the
+    // four channels this thread touches, are fixed: scale/shift live in registers, the loop is LDS.128 / 8 flops / STS.128
+    const int tid = threadIdx.x - 192;
+    const int j = tid & 7, p0 = tid >> 3;
+    const int cgrp = (j ^ (p0 & 7)) << 2;
+    const int npx = p.halo_w * p.halo_h;
+    Ring r(p.stages);
+    TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
+    for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, r.next(), ti.next()) {
+      const int ys0 = ti.ty * kTH + oy_off, xs0 = ti.tx * kTW + ox_off;
+      const bool interior = ys0 >= 0 && xs0 >= 0 && ys0 + p.halo_h <= p.Hin && xs0 + p.halo_w <= p.Win;
+      mbar_wait(&full[r.st], r.ph);
+      uint8_t* sa = s_a + (size_t)r.st * stage_bytes;
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        const float4 a = *reinterpret_cast<const float4*>(bn_a + ch * kKC + cgrp);
+        const float4 b = *reinterpret_cast<const float4*>(bn_b + ch * kKC + cgrp);
+        float4* q = reinterpret_cast<float4*>(sa + (size_t)ch * p.halo_bytes) + tid;
+        if (interior) {
+          int pxl = p0;
+          for (; pxl + 48 < npx; pxl += 64, q += 512) {     // 4 independent items in flight
+            float4 v0 = q[0], v1 = q[128], v2 = q[256], v3 = q[384];
+            v0.x = fmaxf(fmaf(v0.x, a.x, b.x), 0.f); v0.y = fmaxf(fmaf(v0.y, a.y, b.y), 0.f); v0.z = fmaxf(fmaf(v0.z, a.z, b.z), 0.f); v0.w = fmaxf(fmaf(v0.w, a.w, b.w), 0.f);
+            v1.x = fmaxf(fmaf(v1.x, a.x, b.x), 0.f); v1.y = fmaxf(fmaf(v1.y, a.y, b.y), 0.f); v1.z = fmaxf(fmaf(v1.z, a.z, b.z), 0.f); v1.w = fmaxf(fmaf(v1.w, a.w, b.w), 0.f);
+            v2.x = fmaxf(fmaf(v2.x, a.x, b.x), 0.f); v2.y = fmaxf(fmaf(v2.y, a.y, b.y), 0.f); v2.z = fmaxf(fmaf(v2.z, a.z, b.z), 0.f); v2.w = fmaxf(fmaf(v2.w, a.w, b.w), 0.f);
+            v3.x = fmaxf(fmaf(v3.x, a.x, b.x), 0.f); v3.y = fmaxf(fmaf(v3.y, a.y, b.y), 0.f); v3.z = fmaxf(fmaf(v3.z, a.z, b.z), 0.f); v3.w = fmaxf(fmaf(v3.w, a.w, b.w), 0.f);
+            q[0] = v0; q[128] = v1; q[256] = v2; q[384] = v3;
+          }
+          for (; pxl < npx; pxl += 16, q += 128) {
+            float4 v = *q;
+            v.x = fmaxf(fmaf(v.x, a.x, b.x), 0.f); v.y = fmaxf(fmaf(v.y, a.y, b.y), 0.f);
+            v.z = fmaxf(fmaf(v.z, a.z, b.z), 0.f); v.w = fmaxf(fmaf(v.w, a.w, b.w), 0.f);
+            *q = v;
+          }
+        } else {     // image border: pixels outside the input stay zero (SAME padding of the NORMALISED tensor)
+          for (int pxl = p0; pxl < npx; pxl += 16, q += 128) {
+            const int hy = (int)(((uint32_t)pxl * p.div_halo_w) >> 16), hx = pxl - hy * p.halo_w;
+            if ((unsigned)(ys0 + hy) < (unsigned)p.Hin && (unsigned)(xs0 + hx) < (unsigned)p.Win) {
+              float4 v = *q;
+              v.x = fmaxf(fmaf(v.x, a.x, b.x), 0.f); v.y = fmaxf(fmaf(v.y, a.y, b.y), 0.f);
+              v.z = fmaxf(fmaf(v.z, a.z, b.z), 0.f); v.w = fmaxf(fmaf(v.w, a.w, b.w), 0.f);
+              *q = v;
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xready[r.st]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// weights (any strides) -> [tap][n_pad][cin] fp32, zero rows for co >= Cout
+__global__ void __launch_bounds__(256) halo_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wk, int taps, int cin,
+                                                                int cout, int n_pad, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * n_pad * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % n_pad);
+    const int tap = (int)(i / ((long long)cin * n_pad));
+    wk[i] = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_finalize_stats_kernel(const float* __restrict__ partial, int nparts, int n_pad, int C,
+                                                                  long long P, float eps, float* __restrict__ out) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = lane; i < nparts; i += 32) { a += (double)partial[((size_t)i * n_pad + c) * 2]; b += (double)partial[((size_t)i * n_pad + c) * 2 + 1]; }
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane != 0) return;
+  const double mean = a / (double)P;
+  double var = b / (double)P - mean * mean;
+  if (var < 0.0) var = 0.0;
+  out[2 * c] = (float)mean; out[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+int halo_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn halo_get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// shared-memory plan of one launch; returns false when the layer does not fit
+struct HaloPlan {
+  int n_tile, chunks, nky_max, nkx_max, halo_w, halo_h, stages, ctas_per_sm;
+  uint32_t halo_bytes, b_tap_bytes, w_bytes;
+  size_t smem;
+};
+
+bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl) {
+  if (!d) return false;
+  if (d->c_in % kKC != 0 || d->c_in > kMaxCin || d->c_in < kKC) return false;
+  if (d->mode != 0 && d->mode != 1) return false;
+  if (d->mode == 0 && d->stride != 1) return false;
+  if (d->mode == 1 && (d->stride < 1 || d->stride > 2 || d->h_out % d->stride || d->w_out % d->stride)) return false;
+  if (d->in_c_stride % 4 != 0 || d->accumulate != 0 || d->epilogue < 0 || d->epilogue > 2) return false;
+  const int s = d->mode == 1 ? d->stride : 1;
+  const bool small_out = d->c_out <= 4 && d->out_c_stride == 4;                       // prediction head
+  const bool wide_out = (d->c_out == 32 || d->c_out == 64) && d->out_c_stride % 4 == 0 && d->epilogue <= 1;
+  if (!small_out && !wide_out) return false;
+  pl->n_tile = small_out ? 16 : d->c_out;
+  pl->chunks = d->c_in / kKC;
+  pl->nky_max = (d->kh + s - 1) / s; pl->nkx_max = (d->kw + s - 1) / s;
+  if (pl->nky_max * pl->nkx_max > 9) return false;
+  pl->halo_w = kTW + pl->nkx_max - 1; pl->halo_h = kTH + pl->nky_max - 1;
+  pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * 128u + 1023u) & ~1023u;
+  pl->b_tap_bytes = ((uint32_t)pl->n_tile * 128u + 1023u) & ~1023u;
+  pl->w_bytes = (uint32_t)(pl->nky_max * pl->nkx_max * pl->chunks) * pl->b_tap_bytes;
+  const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + 4 * 32 * kStgPitch * sizeof(float);
+  const size_t stage = (size_t)pl->chunks * pl->halo_bytes;
+  const size_t budget2 = 112 * 1024, budget1 = 224 * 1024;
+  static int force_ctas = -1, max_stages = -1;   // measurement knobs
+  if (force_ctas < 0) { const char* e = getenv("LSI_B200_HALO_CTAS"); force_ctas = e ? atoi(e) : 0; }
+  if (max_stages < 0) { const char* e = getenv("LSI_B200_HALO_STAGES"); max_stages = e ? atoi(e) : 0; }
+  if (force_ctas != 1 && fixed + 2 * stage <= budget2) {
+    pl->ctas_per_sm = 2;
+    pl->stages = (int)((budget2 - fixed) / stage);
+  } else if (fixed + 2 * stage <= budget1) {
+    pl->ctas_per_sm = 1;
+    pl->stages = (int)((budget1 - fixed) / stage);
+  } else {
+    return false;
+  }
+  if (pl->stages > kMaxStages) pl->stages = kMaxStages;
+  if (max_stages >= 2 && pl->stages > max_stages) pl->stages = max_stages;
+  pl->smem = fixed + (size_t)pl->stages * stage;
+  return true;
+}
+
+size_t halo_stat_part_bytes(int n_tile) { return (size_t)148 * 2 * 4 * n_tile * 2 * sizeof(float) * 2; }
+
+}  // namespace
+}  // namespace lsi
+
+using namespace lsi;
+
+extern "C" int lsi_b200_conv2d_halo_supported(const lsi_b200_conv_desc* d) {
+  HaloPlan pl;
+  return halo_plan(d, &pl) ? 1 : 0;
+}
+
+extern "C" size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc* d) {
+  HaloPlan pl;
+  if (!halo_plan(d, &pl)) return 0;
+  return (size_t)d->kh * d->kw * pl.n_tile * (size_t)d->c_in * sizeof(float) + 512 + halo_stat_part_bytes(pl.n_tile);
+}
+
+extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats, const float* in_bn_beta,
+                                    const float* w, const float* bias, float* out, float* out_bn_stats, float bn_eps,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  LSI_REQUIRE(d && in && w && out && workspace, "NULL pointer argument");
+  HaloPlan pl;
+  LSI_REQUIRE(halo_plan(d, &pl), "shape not supported by the halo-tile tensor-core path");
+  LSI_REQUIRE((in_bn_stats == nullptr) == (in_bn_beta == nullptr), "in_bn_stats and in_bn_beta go together");
+  LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
+  LSI_REQUIRE(!out_bn_stats || (d->epilogue == 0 && pl.n_tile == d->c_out), "bn statistics need a plain 32/64-channel conv output");
+  LSI_REQUIRE(workspace_bytes >= lsi_b200_conv2d_halo_workspace_bytes(d), "workspace too small");
+  LSI_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "tensors must be 16-byte aligned");
+  LSI_REQUIRE(d->epilogue == 0 || pl.n_tile == 16 || ((uintptr_t)bias & 15) == 0, "bias must be 16-byte aligned");
+  EncodeTiledFn encode = halo_get_encode();
+  LSI_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cudaStream_t st = as_stream(stream);
+
+  const int s = d->mode == 1 ? d->stride : 1;
+  HaloParams p;
+  p.out = out; p.bias = bias; p.in_stats = in_bn_stats; p.in_beta = in_bn_beta; p.stat_part = nullptr;
+  p.Hin = d->h_in; p.Win = d->w_in; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
+  p.Hp = d->h_out / s; p.Wp = d->w_out / s;
+  p.tiles_x = (p.Wp + kTW - 1) / kTW;
+  const int tiles_y = (p.Hp + kTH - 1) / kTH;
+  p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
+  p.chunks = pl.chunks; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
+  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages;
+  p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
+  p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
+
+  // weights -> K-major [tap][n_tile][cin]
+  float* wk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  const int taps = d->kh * d->kw;
+  {
+    const long long total = (long long)taps * pl.n_tile * d->c_in;
+    long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+    halo_prep_weights_kernel<<<(unsigned)g, 256, 0, st>>>(w, wk, taps, d->c_in, d->c_out, pl.n_tile, d->w_tap_stride, d->w_ci_stride,
+                                                          d->w_co_stride);
+    LSI_LAUNCH_CHECK();
+  }
+  CUtensorMap map_a, map_w;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->c_in, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_c_stride * 4, (cuuint64_t)d->w_in * d->in_c_stride * 4,
+                             (cuuint64_t)d->h_in * d->w_in * d->in_c_stride * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)pl.halo_w, (cuuint32_t)pl.halo_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return LSI_B200_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * pl.n_tile};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)pl.n_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
+  }
+  static size_t smem_set = 0;
+  if (pl.smem > smem_set) {
+    LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    smem_set = pl.smem;
+  }
+  const int G = s * s;
+  int n_ctas = halo_num_sms() * pl.ctas_per_sm;
+  if (n_ctas > p.spatial_tiles * G) n_ctas = p.spatial_tiles * G;
+  n_ctas = n_ctas / G * G;
+  if (n_ctas < G) n_ctas = G;
+  if (out_bn_stats) {
+    p.stat_part = wk + (size_t)taps * pl.n_tile * d->c_in;
+    p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
+  }
+  {
+    ScopedTiming tm(kConvTc, st);
+    conv_halo_kernel<<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_w, p);
+  }
+  LSI_LAUNCH_CHECK();
+  if (out_bn_stats) {
+    halo_finalize_stats_kernel<<<(d->c_out + 7) / 8, 256, 0, st>>>(p.stat_part, n_ctas * 4, pl.n_tile, d->c_out,
+                                                                  (long long)d->batch * d->h_out * d->w_out, bn_eps, out_bn_stats);
+    LSI_LAUNCH_CHECK();
+  }
+  return LSI_B200_OK;
+}

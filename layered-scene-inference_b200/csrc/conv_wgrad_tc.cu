@@ -84,6 +84,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of a converged warp, in a form that lets ptxas keep the guarded region's tcgen05/TMA operands in uniform
+// registers (see conv_tc.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "@P1 mov.s32 %0, 1;\n"
+      "}\n" : "+r"(pred));
+  return pred != 0;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_big, const __grid_constant__ CUtensorMap map_small, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -123,7 +136,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_big, const __grid_consta
 
   if (n_iters > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         // ---------------- TMA producer ----------------
         const int per_img = p.tiles_x * p.tiles_y;
         for (int it = 0; it < n_iters; ++it) {
@@ -148,7 +161,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_big, const __grid_consta
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         // ---------------- MMA issuer ----------------
         // D=F32, A=B=TF32, both MN-major (bits 15, 16), N>>3, M>>4
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_cols >> 3) << 17) |
@@ -159,9 +172,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_big, const __grid_consta
           mbar_wait(&full[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + kMBlocks * kBlkBytes;
+          const uint64_t ad = umma_desc_mn(sa), bd = umma_desc_mn(sb);   // + (bytes >> 4) advances the start address
 #pragma unroll
           for (int kk = 0; kk < kPix / 8; ++kk)     // one UMMA per group of 8 pixels (1024 bytes down the tile)
-            umma_tf32(tmem_base, umma_desc_mn(sa + kk * 1024), umma_desc_mn(sb + kk * 1024), idesc, (it | kk) != 0);
+            umma_tf32(tmem_base, ad + 64 * kk, bd + 64 * kk, idesc, (it | kk) != 0);
           umma_commit(&empty[st]);
         }
         umma_commit(tmem_full);

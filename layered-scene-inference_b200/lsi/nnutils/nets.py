@@ -15,6 +15,7 @@ inference-mode batch norm (the reference never updates the moving averages, trai
 batch statistics, ldi_pred_eval.py:45).
 """
 import math
+import os
 import zlib
 
 import numpy as np
@@ -212,6 +213,58 @@ def _wgrad(desc_kw, big, small, dw):
     _b200.call('lsi_b200_conv2d_wgrad', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
 
 
+_HALO = os.environ.get('LSI_B200_CONV_HALO', '1') != '0'
+
+
+def set_halo_mode(on):
+    """Inference path only: route the full-resolution few-channel head layers through the halo-tile kernel
+    (lsi_b200_conv2d_halo: resident weights, one TMA halo box per tile, the producer's batch norm + ReLU applied on
+    load) instead of the generic tensor-core kernel + a separate normalise pass.  Default on (LSI_B200_CONV_HALO=0
+    disables)."""
+    global _HALO
+    _HALO = bool(on)
+
+
+class _Pending(object):
+    """RAW output of a slim.conv2d whose batch_norm + ReLU (nets.py:263-272) has not been applied yet: z [B,H,W,C],
+    stats [C,2] = (mean, rstd), beta [C].  Exists only on the no-grad inference path, between a producing conv and a
+    consumer that normalises on load; `materialize()` applies it in place for every other consumer."""
+
+    def __init__(self, z, stats, beta):
+        self.z, self.stats, self.beta = z, stats, beta
+        self.shape = z.shape
+        self.device = z.device
+
+    def materialize(self):
+        z = self.z
+        B, H, W, C = z.shape
+        _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(self.beta), _b200.ptr(z), _b200.ptr(self.stats),
+                   B * H * W, C, C, C, BN_EPS, 1, 1, _b200.ptr(_bn_workspace(z.device, C)), _b200.stream())
+        return z
+
+
+def _materialize(x):
+    return x.materialize() if isinstance(x, _Pending) else x
+
+
+def _halo_ok(d, *tensors):
+    return (_HALO and _CONV_MODE == 'tf32' and not torch.is_grad_enabled()
+            and _b200.lib().lsi_b200_conv2d_halo_supported(d) == 1
+            and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
+
+
+def _conv_halo(d, x, w, out, bias=None, out_stats=None):
+    """One halo-tile launch; x: tensor or _Pending (normalised on load)."""
+    lib = _b200.lib()
+    pend = isinstance(x, _Pending)
+    xin = x.z if pend else x
+    nws = int(lib.lsi_b200_conv2d_halo_workspace_bytes(d))
+    ws = _tc_workspace(xin.device, nws)
+    _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(xin), _b200.ptr(x.stats) if pend else None,
+               _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out), _b200.ptr(out_stats),
+               BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+
+
 class _Geometry(object):
     """Descriptors of one layer: forward, data gradient, weight gradient."""
 
@@ -351,26 +404,47 @@ def ctypes_offset(t, n_floats):
     return ctypes.c_void_p(t.data_ptr() + 4 * n_floats)
 
 
-def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False):
+def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer=False):
     """conv / up-conv + batch-stat BN + ReLU.  `x` may be a pair (a, b) standing for tf.concat([a, b], axis=3): under
-    no_grad the tensor-core kernel reads the two sources directly; with autograd the concat is materialised."""
-    if isinstance(x, (tuple, list)):
-        a, b = (_b200.dev_f32(t, scope + ' input') for t in x)
-        B, H, W, ca = a.shape
-        cin = ca + b.shape[3]
+    no_grad the tensor-core kernel reads the two sources directly; with autograd the concat is materialised.
+    Inference path (no_grad, tensor-core mode): the conv writes its RAW output and reduces the batch statistics in its
+    epilogue; with defer=True the normalise + ReLU pass is left to the consumer (`_Pending`), otherwise it runs in
+    place.  A `_Pending` input is normalised on load when the halo-tile kernel supports the layer."""
+    if not torch.is_grad_enabled() and _CONV_MODE == 'tf32':
+        pair = isinstance(x, (tuple, list))
+        if pair:
+            a, b = (_b200.dev_f32(_materialize(t), scope + ' input') for t in x)
+            ca, cin = a.shape[3], a.shape[3] + b.shape[3]
+        else:
+            a = x if isinstance(x, _Pending) else _b200.dev_f32(x, scope + ' input')
+            b, ca, cin = None, a.shape[3], a.shape[3]
+        B, H, W = a.shape[0], a.shape[1], a.shape[2]
         geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
         w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
         beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
         d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=ca))
-        if not torch.is_grad_enabled() and _tc_ok(d, ca, a, b):
-            dev = a.device
+        dev = a.device
+        done = False
+        if not pair and _halo_ok(d, a.z if isinstance(a, _Pending) else a):
             z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float32, device=dev)
             stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
-            have = _conv(dict(geo.fwd, in_c_stride=ca), a, w, z, bn_stats=stats, inp_b=b, c_in_a=ca)
-            _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(z), _b200.ptr(stats),
-                       B * geo.Ho * geo.Wo, cout, cout, cout, BN_EPS, 1, 1 if have else 0,
-                       _b200.ptr(_bn_workspace(dev, cout)), _b200.stream())      # in place: nothing is kept for a backward
-            return z
+            _conv_halo(d, a, w, z, out_stats=stats)
+            done = True
+        else:
+            a = _materialize(a)
+            if _tc_ok(d, ca, a, b):
+                z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float32, device=dev)
+                stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
+                have = _conv(dict(geo.fwd, in_c_stride=ca), a, w, z, bn_stats=stats, inp_b=b, c_in_a=ca)
+                if not have:       # cannot happen on the tensor-core path; keep the contract explicit
+                    raise RuntimeError('lsi_b200: conv epilogue did not produce batch statistics')
+                done = True
+            x = (a, b) if pair else a
+        if done:
+            out = _Pending(z, stats, beta)
+            return out if defer else out.materialize()
+    if isinstance(x, (tuple, list)):
+        a, b = (_b200.dev_f32(t, scope + ' input') for t in x)
         x = _ConcatChannels.apply(a, b)
     x = _b200.dev_f32(x, scope + ' input')
     B, H, W, cin = x.shape
@@ -383,7 +457,8 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False):
 # ---------------------------------------------------------------------------------------------------------------------
 # the reference's public functions
 # ---------------------------------------------------------------------------------------------------------------------
-def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False, _scope='decoder', _store=None):
+def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False, _scope='decoder', _store=None,
+                   _defer=False):
     """nets.py:73-114 -- nconv x [4x4 s2 up-conv -> concat skip -> 3x3 conv].  Returns (feat, end_points)."""
     _require_training(is_training)
     store = _store or get_default_store()
@@ -391,10 +466,10 @@ def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False,
     end_points = {}
     for nc in range(nconv, 0, -1):
         n_filt = n_filters[nc - 1]
-        feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True)
+        feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True, defer=_defer)
         if nc > 1 and skip_feat is not None:
             feat = (feat, skip_feat[-nc + 1])                    # tf.concat([feat, skip], axis=3), nets.py:108-109
-        feat = _conv_layer(store, '%s/upcnv%db' % (_scope, nc), feat, n_filt, 3, 1, reuse)
+        feat = _conv_layer(store, '%s/upcnv%db' % (_scope, nc), feat, n_filt, 3, 1, reuse, defer=_defer)
         end_points['%s/upcnv%db' % (_scope, nc)] = feat
     return feat, end_points
 
@@ -408,13 +483,21 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
     preds = []
     for l in range(n_layers):
         base = '%s/upsample_%d' % (_scope, l)
+        # _defer: inside this function nothing but the next conv sees the decoder features, so (inference path) their
+        # batch norm + ReLU may stay pending and be applied on load by the consumer
         feat_l, _ = decoder_simple(feat, nconv=n_layerwise_steps, skip_feat=skip_feat, reuse=reuse, is_training=is_training,
-                                   _scope=base + '/decoder', _store=store)
+                                   _scope=base + '/decoder', _store=store, _defer=True)
         B, H, W, cin = feat_l.shape
         geo = _Geometry(False, B, H, W, cin, nc, 3, 1, out_hw=_out_hw)
         w = store.get('%s/pred_%d/weights' % (base, l), geo.w_shape, reuse, 'weights')
         b = store.get('%s/pred_%d/biases' % (base, l), [nc], reuse, 'biases')
-        preds.append(_ConvBiasSigmoid.apply(feat_l, w, b, geo))
+        dp = _b200.ConvDesc(**dict(geo.fwd, epilogue=2))
+        if _halo_ok(dp, feat_l.z if isinstance(feat_l, _Pending) else feat_l):
+            y = torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
+            _conv_halo(dp, feat_l, w, y, bias=b)
+            preds.append(y)
+        else:
+            preds.append(_ConvBiasSigmoid.apply(_materialize(feat_l), w, b, geo))
     return torch.stack(preds, dim=0), {}
 
 

@@ -1,0 +1,136 @@
+"""GPU: the halo-tile tensor-core convolution (lsi_b200_conv2d_halo: resident weights, one TMA halo box per tile,
+producer's batch norm + ReLU applied on load, batch statistics + coalesced stores in the epilogue) against the fp32
+CUDA-core kernel (lsi_b200_conv2d) fed with the explicitly normalised input.  TF32 inputs, fp32 accumulation:
+tolerance 2e-3 of the output scale (same bar as tests/test_gpu_conv_tc.py)."""
+import pytest
+import torch
+
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+EPS = 1e-3
+
+
+def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=None, seed=0):
+    from lsi import _b200
+    from lsi.nnutils.nets import same_pad
+    lib = _b200.lib()
+    torch.manual_seed(seed)
+    dev = 'cuda'
+    if mode == 0:
+        Ho, Wo = (Hi, Wi) if out_hw is None else out_hw
+        s, pt, pl = 1, same_pad(Hi, k, 1)[0], same_pad(Wi, k, 1)[0]
+        w = torch.randn(k, k, Cin, Cout, device=dev) / (k * k * Cin) ** 0.5
+        ws = dict(w_tap_stride=Cin * Cout, w_ci_stride=Cout, w_co_stride=1)
+    else:                      # 4x4 stride-2 up-convolution, weights [kh,kw,cout,cin]
+        assert k == 4
+        Ho, Wo, s, pt, pl = 2 * Hi, 2 * Wi, 2, 1, 1
+        w = torch.randn(k, k, Cout, Cin, device=dev) / (4 * Cin) ** 0.5
+        ws = dict(w_tap_stride=Cin * Cout, w_ci_stride=1, w_co_stride=Cin)
+    x = torch.randn(B, Hi, Wi, Cin, device=dev) * 1.7 + 0.3
+    bias = torch.randn(max(Cout, 4), device=dev)
+    kw = dict(batch=B, h_in=Hi, w_in=Wi, c_in=Cin, h_out=Ho, w_out=Wo, c_out=Cout, kh=k, kw=k, stride=s, pad_top=pt,
+              pad_left=pl, mode=mode, in_c_stride=Cin, out_c_stride=Cout, epilogue=epilogue, accumulate=0, **ws)
+    d = _b200.ConvDesc(**kw)
+    assert lib.lsi_b200_conv2d_halo_supported(d) == 1
+    if bn_in:
+        mean = x.mean(dim=(0, 1, 2)); var = x.var(dim=(0, 1, 2), unbiased=False)
+        in_stats = torch.stack([mean, torch.rsqrt(var + EPS)], dim=1).contiguous()
+        beta = torch.randn(Cin, device=dev) * 0.5
+        xn = torch.relu((x - mean) * in_stats[:, 1] + beta).contiguous()
+    else:
+        in_stats = beta = None
+        xn = x
+    ref = torch.zeros(B, Ho, Wo, Cout, device=dev)
+    _b200.call('lsi_b200_conv2d', d, _b200.ptr(xn), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(ref), _b200.stream())
+    out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev)
+    st = torch.zeros(Cout, 2, device=dev) if stats_out else None
+    nws = lib.lsi_b200_conv2d_halo_workspace_bytes(d)
+    wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
+    _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w), _b200.ptr(bias),
+               _b200.ptr(out), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
+    torch.cuda.synchronize()
+    return out, ref, st
+
+
+def _check(out, ref, st):
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+    if st is not None:
+        mean = ref.mean(dim=(0, 1, 2)); var = ref.var(dim=(0, 1, 2), unbiased=False)
+        assert rel_err(st[:, 0].cpu(), mean.cpu()) < TOL
+        assert rel_err(st[:, 1].cpu(), torch.rsqrt(var + EPS).cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,bn_in', [
+    (1, 16, 8, False),        # exactly one tile
+    (1, 16, 8, True),
+    (2, 21, 37, True),        # ragged: partial tiles on both edges
+    (1, 48, 40, False),
+    (4, 128, 160, True),      # 640 tiles: several tiles per persistent CTA, the ring wraps
+])
+def test_conv3x3_32to32(B, H, W, bn_in):
+    _check(*_run(B, H, W, 32, 32, 3, 0, bn_in, True))
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,bn_in', [
+    (1, 8, 4, 64, 32, False),     # one tile per phase
+    (2, 16, 24, 64, 32, True),    # head layer upcnv1
+    (1, 19, 11, 64, 32, True),    # ragged
+    (3, 64, 112, 64, 32, True),   # many tiles per CTA
+    (1, 16, 16, 32, 32, True),
+    (1, 24, 16, 64, 64, True),
+])
+def test_upconv_4x4_s2(B, H, W, Cin, Cout, bn_in):
+    _check(*_run(B, H, W, Cin, Cout, 4, 1, bn_in, True))
+
+
+@pytest.mark.parametrize('B,H,W,out_hw,bn_in', [
+    (1, 16, 8, None, False),
+    (2, 32, 48, (32, 40), True),      # crop fused into the prediction conv
+    (2, 128, 128, (128, 104), True),
+])
+def test_prediction_conv_bias_sigmoid(B, H, W, out_hw, bn_in):
+    out, ref, _ = _run(B, H, W, 32, 4, 3, 0, bn_in, False, epilogue=2, out_hw=out_hw)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+def test_conv_bias_epilogue_64_channels():
+    out, ref, _ = _run(2, 32, 24, 32, 64, 3, 0, True, False, epilogue=1)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+def test_heads_match_generic_path():
+    """The whole inference pipeline with the halo kernel on vs off (both TF32): same LDI within TF32 noise."""
+    from lsi.nnutils import nets
+    torch.manual_seed(0)
+    store = nets.ParamStore()
+    img = torch.rand(2, 128, 128, 3, device='cuda')
+    outs = []
+    for on in (False, True):
+        nets.set_halo_mode(on)
+        with torch.no_grad():
+            _, fd, sk, _ = nets.encoder_decoder_unet(img, nl_diff_enc_dec=3, reuse=on, _store=store)
+            tex, _, disp = nets.ldi_predictor(fd, n_layers=2, reuse=on, n_layerwise_steps=3, skip_feat=sk, _store=store)
+        outs.append((tex.clone(), disp.clone()))
+    nets.set_halo_mode(True)
+    for a, b in zip(outs[0], outs[1]):
+        d = (a - b).abs()
+        assert float(d.max()) < 2e-2 and float(d.mean()) < 1e-3, (float(d.max()), float(d.mean()))
+
+
+def test_unsupported_shapes_are_refused():
+    from lsi import _b200
+    lib = _b200.lib()
+    base = dict(batch=1, h_in=16, w_in=16, c_in=32, h_out=16, w_out=16, c_out=32, kh=3, kw=3, stride=1, pad_top=1, pad_left=1,
+                mode=0, w_tap_stride=1024, w_ci_stride=32, w_co_stride=1, in_c_stride=32, out_c_stride=32, epilogue=0,
+                accumulate=0)
+    assert lib.lsi_b200_conv2d_halo_supported(_b200.ConvDesc(**base)) == 1
+    for bad in (dict(c_in=3, in_c_stride=4), dict(c_in=256, in_c_stride=256), dict(stride=2, h_out=8, w_out=8),
+                dict(c_out=128, out_c_stride=128), dict(kh=7, kw=7, pad_top=3, pad_left=3), dict(accumulate=1)):
+        assert lib.lsi_b200_conv2d_halo_supported(_b200.ConvDesc(**dict(base, **bad))) == 0, bad
+    d = _b200.ConvDesc(**dict(base, c_out=128, out_c_stride=128))
+    x = torch.zeros(1, 16, 16, 32, device='cuda')
+    with pytest.raises(RuntimeError):
+        _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), None, None, _b200.ptr(x), None, _b200.ptr(x), None, EPS,
+                   _b200.ptr(x), 4, _b200.stream())
