@@ -288,44 +288,36 @@ def main():
     renderer_only = B / (r0.elapsed_time(r1) / 20 * 1e-3)
     del ldi_fixed
 
-    # --- end to end through the public API with HOST buffers: H2D of images + cameras, CNN, render, D2H of the views --
-    pin_img = torch.tensor(img_host).pin_memory()
-    pin_cam = [torch.tensor(host[k]).pin_memory() for k in ('k_s', 'k_t', 'rot', 't')]
-    out_img = torch.empty(1, B, int(H * DS), int(W * DS), 3).pin_memory()
-    out_wts = torch.empty(1, B, int(H * DS), int(W * DS), 1).pin_memory()
-
-    def e2e_step():
-        with torch.no_grad():
-            x = pin_img.to(dev, non_blocking=True)
-            c = [t.to(dev, non_blocking=True) for t in pin_cam]
-            ldi = train_utils.predict_ldi(x, opts, store, reuse=True)
-            img, wts = ldi_utils.forward_splat(tuple(ldi), pc, *c, **kw)
-            out_img.copy_(img, non_blocking=True)
-            out_wts.copy_(wts, non_blocking=True)
-        torch.cuda.synchronize()
-
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    # --- end to end through the public API with HOST buffers: every step copies its images + cameras host->device and its
+    #     rendered views device->host (train_utils.HostViewPipeline: the copies of neighbouring steps overlap the kernels) ----
+    del imgs
+    torch.cuda.empty_cache()
+    hbatch = {'img': torch.tensor(img_host).pin_memory()}
+    for name, key in (('k_s', 'k_s'), ('k_t', 'k_t'), ('rot', 'rot'), ('t', 't')):
+        hbatch[name] = torch.tensor(host[key]).pin_memory()
+    pipe = train_utils.HostViewPipeline(opts, store, kw, B, H, W, dev, depth=2)
+    checks = []
+    e2e_steps = max(5, min(args.steps, 10))
+    pipe.run([hbatch] * 3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    pipe.run([hbatch] * e2e_steps, on_result=lambda k, im, wt: checks.append(float(im[0, 0, 0, 0, 0])))
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert len(checks) == e2e_steps and all(np.isfinite(c) for c in checks)
     if dist is not None:
         tt = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = tt.item()
-    h2d = pin_img.numel() * 4 + sum(t.numel() * 4 for t in pin_cam)
-    d2h = (out_img.numel() + out_wts.numel()) * 4
-    e2e = {'value': world * B / e2e_s, 'unit': 'views/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-           'ms_per_step': e2e_s * 1e3, 'api': 'lsi.nnutils.train_utils.predict_ldi + lsi.geometry.ldi.forward_splat on pinned host '
-                                              'images/cameras, rendered views copied back'}
+    e2e = {'value': world * B / e2e_s, 'unit': 'views/s', 'h2d_bytes_per_step': pipe.h2d_bytes(hbatch),
+           'd2h_bytes_per_step': pipe.d2h_bytes(), 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps,
+           'api': 'lsi.nnutils.train_utils.HostViewPipeline.run (predict_ldi + lsi.geometry.ldi.forward_splat per batch) on pinned '
+                  'host images/cameras, rendered views copied back to pinned host memory every step; H2D of step k+1 and D2H of '
+                  'step k-1 overlap the kernels of step k'}
+    del pipe
 
     # --- training step at BASELINE config 4's per-GPU shard (batch 8 per GPU, 256x832, L=4): two towers, view-synthesis
     #     loss, backward, ONE all-reduce of the flat gradient buffer (NCCL, when world > 1), fused Adam -------------------
-    del imgs, pin_img, out_img, out_wts
     torch.cuda.empty_cache()
     tb = 8
     topts = train_utils.default_opts(dataset='kitti', n_layers=L, batch_size=tb, img_height=H, img_width=W)

@@ -133,7 +133,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   // carve: [resident weights][stages x chunks x halo tile][barriers 256 B][bn scale/shift 2 x 512 B][staging 4 x 32 x 36 floats]
-  const uint32_t stage_bytes = (uint32_t)p.chunks * p.halo_bytes;
+  const uint32_t stage_bytes = p.halo_bytes;     // one stage = one 32-channel chunk of one tile's halo
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + p.w_bytes;
   uint8_t* s_ctl = s_a + (size_t)p.stages * stage_bytes;
@@ -199,15 +199,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
                         ((ky0 + i * s) * p.kw + (kx0 + j * s)) * p.n_tile);
       Ring r(p.stages);
-      const uint32_t tx = (uint32_t)p.chunks * (uint32_t)(p.halo_w * p.halo_h) * 128u;
+      const uint32_t tx = (uint32_t)(p.halo_w * p.halo_h) * 128u;
       TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
-      for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, r.next(), ti.next()) {
+      for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ti.next()) {
         const int n_img = ti.n, y0 = ti.ty * kTH, x0 = ti.tx * kTW;
-        mbar_wait(&empty[r.st], r.ph ^ 1);
-        mbar_expect_tx(&full[r.st], tx);
-        const uint32_t sa = smem_u32(s_a) + (uint32_t)r.st * stage_bytes;
-        for (int ch = 0; ch < p.chunks; ++ch)
-          tma_load_4d(sa + (uint32_t)ch * p.halo_bytes, &map_a, &full[r.st], ch * kKC, x0 + ox_off, y0 + oy_off, n_img);
+        for (int ch = 0; ch < p.chunks; ++ch, r.next()) {
+          mbar_wait(&empty[r.st], r.ph ^ 1);
+          mbar_expect_tx(&full[r.st], tx);
+          tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_a, &full[r.st], ch * kKC, x0 + ox_off, y0 + oy_off, n_img);
+        }
       }
     }
   } else if (warp == 1) {
@@ -220,22 +220,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint64_t b_desc0 = umma_desc(hi_b, smem_u32(s_w));
       Ring r(p.stages);
       int tcount = 0;
-      for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, r.next(), ++tcount) {
+      for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ++tcount) {
         const int buf = tcount & 1;
         mbar_wait(&tmem_empty[buf], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
-        mbar_wait(bn_in ? &xready[r.st] : &full[r.st], r.ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
-        // descriptors advance by adding byte offsets >> 4 to the start-address field (no carry out of its 14 bits:
-        // every operand lives below 256 KB)
-        const uint64_t a_desc0 = umma_desc(hi_a, smem_u32(s_a) + (uint32_t)r.st * stage_bytes);
         uint32_t acc = 0;
-        for (int ch = 0; ch < p.chunks; ++ch) {
+        for (int ch = 0; ch < p.chunks; ++ch, r.next()) {
+          mbar_wait(bn_in ? &xready[r.st] : &full[r.st], r.ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // descriptors advance by adding byte offsets >> 4 to the start-address field (no carry out of its 14 bits:
+          // every operand lives below 256 KB)
+          const uint64_t a_desc0 = umma_desc(hi_a, smem_u32(s_a) + (uint32_t)r.st * stage_bytes);
           for (int i = 0; i < nky; ++i) {
             const int dy = (p.mode == 0) ? i : nky - 1 - i;
             for (int j = 0; j < nkx; ++j) {
               const int dx = (p.mode == 0) ? j : nkx - 1 - j;
-              const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)ch * p.halo_bytes + (uint32_t)(dy * p.halo_w + dx) * 128u) >> 4);
+              const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * 128u) >> 4);
               const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes) >> 4);
 #pragma unroll
               for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
@@ -244,8 +244,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             }
           }
+          umma_commit(&empty[r.st]);               // frees the stage once these MMAs have read it
         }
-        umma_commit(&empty[r.st]);                 // frees the stage once these MMAs have read it
         umma_commit(&tmem_full[buf]);              // accumulator complete
       }
     }
@@ -361,15 +361,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int npx = p.halo_w * p.halo_h;
     Ring r(p.stages);
     TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
-    for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, r.next(), ti.next()) {
+    for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ti.next()) {
       const int ys0 = ti.ty * kTH + oy_off, xs0 = ti.tx * kTW + ox_off;
       const bool interior = ys0 >= 0 && xs0 >= 0 && ys0 + p.halo_h <= p.Hin && xs0 + p.halo_w <= p.Win;
-      mbar_wait(&full[r.st], r.ph);
-      uint8_t* sa = s_a + (size_t)r.st * stage_bytes;
-      for (int ch = 0; ch < p.chunks; ++ch) {
+      for (int ch = 0; ch < p.chunks; ++ch, r.next()) {
+        mbar_wait(&full[r.st], r.ph);
         const float4 a = *reinterpret_cast<const float4*>(bn_a + ch * kKC + cgrp);
         const float4 b = *reinterpret_cast<const float4*>(bn_b + ch * kKC + cgrp);
-        float4* q = reinterpret_cast<float4*>(sa + (size_t)ch * p.halo_bytes) + tid;
+        float4* q = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes) + tid;
         if (interior) {
           int pxl = p0;
           for (; pxl + 48 < npx; pxl += 64, q += 512) {     // 4 independent items in flight
@@ -397,10 +396,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xready[r.st]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xready[r.st]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -489,7 +488,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl) {
   pl->b_tap_bytes = ((uint32_t)pl->n_tile * 128u + 1023u) & ~1023u;
   pl->w_bytes = (uint32_t)(pl->nky_max * pl->nkx_max * pl->chunks) * pl->b_tap_bytes;
   const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + 4 * 32 * kStgPitch * sizeof(float);
-  const size_t stage = (size_t)pl->chunks * pl->halo_bytes;
+  const size_t stage = (size_t)pl->halo_bytes;   // one 32-channel chunk of one tile's halo
   const size_t budget2 = 112 * 1024, budget1 = 224 * 1024;
   static int force_ctas = -1, max_stages = -1;   // measurement knobs
   if (force_ctas < 0) { const char* e = getenv("LSI_B200_HALO_CTAS"); force_ctas = e ? atoi(e) : 0; }

@@ -78,6 +78,96 @@ def predict_ldi(img, opts, store, reuse):
     return [tex, masks, disps * opts.max_disp]
 
 
+class HostViewPipeline(object):
+    """Image -> LDI -> rendered target view (the predict + render path of ldi_pred_eval.py:117-224) over a sequence of
+    HOST batches.  Three CUDA streams: while batch k runs its kernels, batch k+1's images and cameras are copied
+    host->device and batch k-1's rendered views device->host (PCIe is full duplex), through `depth` device input
+    buffers and `depth` pinned host output buffers.  Every byte of every batch still crosses the bus; only the
+    waiting is removed.  The arithmetic of a batch is exactly predict_ldi + forward_splat (batch-norm statistics stay
+    per batch).
+
+    batches: sequence of dicts of pinned host tensors {'img' [B,H,W,3], 'k_s','k_t','rot' [B,3,3], 't' [B,3] or [B,3,1]}.
+    on_result(k, img_host, wts_host) is called once batch k's views are in host memory (the buffers are recycled
+    after the callback returns)."""
+
+    def __init__(self, opts, store, render_kw, batch, height, width, device, depth=2):
+        from lsi.geometry import ldi as ldi_utils
+        self._render = ldi_utils.forward_splat
+        self.opts, self.store, self.kw, self.device, self.depth = opts, store, dict(render_kw), torch.device(device), depth
+        ds = float(render_kw.get('trg_downsampling', 1))
+        ht, wt = int(height * ds), int(width * ds)
+        dev = self.device
+        self.pc = nn_helpers.pixel_coords(batch, height, width, device=dev)
+        self.x = [torch.empty(batch, height, width, 3, device=dev) for _ in range(depth)]
+        self.cams = [dict(k_s=torch.empty(batch, 3, 3, device=dev), k_t=torch.empty(batch, 3, 3, device=dev),
+                          rot=torch.empty(batch, 3, 3, device=dev), t=None) for _ in range(depth)]
+        self.out_img = [torch.empty(1, batch, ht, wt, 3).pin_memory() for _ in range(depth)]
+        self.out_wts = [torch.empty(1, batch, ht, wt, 1).pin_memory() for _ in range(depth)]
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def h2d_bytes(self, batch):
+        return sum(batch[k].numel() * 4 for k in ('img', 'k_s', 'k_t', 'rot', 't'))
+
+    def d2h_bytes(self):
+        return (self.out_img[0].numel() + self.out_wts[0].numel()) * 4
+
+    def run(self, batches, on_result=None):
+        n, depth = len(batches), self.depth
+        cur = torch.cuda.current_stream(self.device)
+        ready, free_in, out_done = [None] * depth, [None] * depth, [None] * depth
+
+        def upload(k):
+            s, b = k % depth, batches[k]
+            with torch.cuda.stream(self.s_in):
+                if free_in[s] is not None:
+                    self.s_in.wait_event(free_in[s])            # batch k - depth has finished reading this buffer
+                self.x[s].copy_(b['img'], non_blocking=True)
+                c = self.cams[s]
+                for key in ('k_s', 'k_t', 'rot'):
+                    c[key].copy_(b[key], non_blocking=True)
+                c['t'] = b['t'].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.s_in)
+                ready[s] = ev
+
+        def deliver(k):
+            s = k % depth
+            out_done[s].synchronize()
+            if on_result is not None:
+                on_result(k, self.out_img[s], self.out_wts[s])
+            out_done[s] = None
+
+        upload(0)
+        for k in range(n):
+            if k + 1 < n:
+                upload(k + 1)
+            s = k % depth
+            cur.wait_event(ready[s])
+            with torch.no_grad():
+                ldi = predict_ldi(self.x[s], self.opts, self.store, reuse=True)
+                c = self.cams[s]
+                c['t'].record_stream(cur)
+                img, wts = self._render(tuple(ldi), self.pc, c['k_s'], c['k_t'], c['rot'], c['t'], **self.kw)[:2]
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            free_in[s] = ev
+            if out_done[s] is not None:
+                deliver(k - depth)                              # the host buffer is about to be overwritten
+            self.s_out.wait_event(ev)
+            with torch.cuda.stream(self.s_out):
+                self.out_img[s].copy_(img, non_blocking=True)
+                self.out_wts[s].copy_(wts, non_blocking=True)
+                img.record_stream(self.s_out)
+                wts.record_stream(self.s_out)
+                evo = torch.cuda.Event()
+                evo.record(self.s_out)
+                out_done[s] = evo
+        for k in range(max(0, n - depth), n):
+            if out_done[k % depth] is not None:
+                deliver(k)
+        cur.synchronize()
+
+
 class Trainer(object):
     """One training step of ldi_enc_dec.py on the B200 path."""
 

@@ -80,6 +80,8 @@ def test_conv3x3_32to32(B, H, W, bn_in):
     (3, 64, 112, 64, 32, True),   # many tiles per CTA
     (1, 16, 16, 32, 32, True),
     (1, 24, 16, 64, 64, True),
+    (2, 32, 24, 128, 64, True),   # head layer upcnv2: four chunk stages per tile, 128 KB of resident weights
+    (1, 16, 8, 128, 64, False),
 ])
 def test_upconv_4x4_s2(B, H, W, Cin, Cout, bn_in):
     _check(*_run(B, H, W, Cin, Cout, 4, 1, bn_in, True))

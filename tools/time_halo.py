@@ -15,6 +15,8 @@ a = ap.parse_args()
 lib = _b200.lib()
 B, H, W = a.batch, a.h, a.w
 layers = [
+    ('upcnv2  128->64 4x4/2 up', dict(h_in=H // 4, w_in=W // 4, c_in=128, h_out=H // 2, w_out=W // 2, c_out=64, kh=4, kw=4, stride=2, pad_top=1, pad_left=1, mode=1,
+                                      w_tap_stride=128 * 64, w_ci_stride=1, w_co_stride=128, in_c_stride=128, out_c_stride=64, epilogue=0), True),
     ('upcnv1  64->32 4x4/2 up', dict(h_in=H // 2, w_in=W // 2, c_in=64, h_out=H, w_out=W, c_out=32, kh=4, kw=4, stride=2, pad_top=1, pad_left=1, mode=1,
                                      w_tap_stride=64 * 32, w_ci_stride=1, w_co_stride=64, in_c_stride=64, out_c_stride=32, epilogue=0), True),
     ('upcnv1b 32->32 3x3', dict(h_in=H, w_in=W, c_in=32, h_out=H, w_out=W, c_out=32, kh=3, kw=3, stride=1, pad_top=1, pad_left=1, mode=0,
