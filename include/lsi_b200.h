@@ -215,13 +215,15 @@ LSI_B200_API int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const f
  * in_bn_stats/in_bn_beta (both or neither): the input is the RAW output of a slim.conv2d whose batch_norm + ReLU
  * (nets.py:263-272) has not been applied yet -- (mean, rstd)[c_in] and beta[c_in]; it is applied on load, in shared
  * memory, so the normalised tensor never exists in HBM.  out_bn_stats (optional, plain c_out in {32,64} convs): receives
- * (mean, rsqrt(biased var + eps)) of this layer's raw output, reduced in the epilogue. */
+ * (mean, rsqrt(biased var + eps)) of this layer's raw output, reduced in the epilogue.  out_scale (optional, <= 4-channel
+ * outputs): per-channel factor applied after the activation -- `disps *= max_disp` of ldi_enc_dec.py:213 fused into the
+ * prediction conv. */
 LSI_B200_API int lsi_b200_conv2d_halo_supported(const lsi_b200_conv_desc* d);
 LSI_B200_API size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc* d);
 LSI_B200_API int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats,
-                                      const float* in_bn_beta, const float* w, const float* bias, float* out,
-                                      float* out_bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
-                                      void* stream);
+                                      const float* in_bn_beta, const float* w, const float* bias, const float* out_scale,
+                                      float* out, float* out_bn_stats, float bn_eps, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 
 /* slim.batch_norm(is_training=True, center=True, scale=False) + ReLU (nets.py:263-272): batch statistics over the
  * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward (stats_given != 0: they were

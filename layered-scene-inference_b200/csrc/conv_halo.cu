@@ -33,7 +33,7 @@ constexpr int kStgPitch = 36;                          // floats per staged pixe
 constexpr int kMaxCin = 128;
 
 struct HaloParams {
-  float* out; const float* bias;
+  float* out; const float* bias; const float* out_scale;   // out_scale: per-channel factor after the activation (small-output path), or NULL
   const float* in_stats; const float* in_beta;   // producer's (mean, rstd)[Cin] and beta[Cin]; NULL = input is final
   float* stat_part;                              // [gridDim.x * 4][n_tile][2] channel sums of the output, or NULL
   int Hin, Win, Ho, Wo, Co, out_cs, Hp, Wp;
@@ -301,6 +301,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               v[j] = __uint_as_float(r[j]);
               if (p.epilogue >= 1 && j < p.Co) v[j] += __ldg(p.bias + j);
               if (p.epilogue == 2) v[j] = 1.f / (1.f + expf(-v[j]));
+              if (p.out_scale && j < p.Co) v[j] *= __ldg(p.out_scale + j);
             }
             float* dst = p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * 4;
             if (p.Co == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -527,8 +528,8 @@ extern "C" size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc*
 }
 
 extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats, const float* in_bn_beta,
-                                    const float* w, const float* bias, float* out, float* out_bn_stats, float bn_eps,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+                                    const float* w, const float* bias, const float* out_scale, float* out, float* out_bn_stats,
+                                    float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
   LSI_REQUIRE(d && in && w && out && workspace, "NULL pointer argument");
   HaloPlan pl;
   LSI_REQUIRE(halo_plan(d, &pl), "shape not supported by the halo-tile tensor-core path");
@@ -544,7 +545,8 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
 
   const int s = d->mode == 1 ? d->stride : 1;
   HaloParams p;
-  p.out = out; p.bias = bias; p.in_stats = in_bn_stats; p.in_beta = in_bn_beta; p.stat_part = nullptr;
+  LSI_REQUIRE(!out_scale || pl.n_tile == 16, "out_scale is supported on the <= 4-channel output path only");
+  p.out = out; p.bias = bias; p.out_scale = out_scale; p.in_stats = in_bn_stats; p.in_beta = in_bn_beta; p.stat_part = nullptr;
   p.Hin = d->h_in; p.Win = d->w_in; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
   p.Hp = d->h_out / s; p.Wp = d->w_out / s;
   p.tiles_x = (p.Wp + kTW - 1) / kTW;

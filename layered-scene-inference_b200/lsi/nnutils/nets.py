@@ -214,6 +214,7 @@ def _wgrad(desc_kw, big, small, dw):
 
 
 _HALO = os.environ.get('LSI_B200_CONV_HALO', '1') != '0'
+_OUT_SCALE_CACHE = {}
 
 
 def set_halo_mode(on):
@@ -253,7 +254,7 @@ def _halo_ok(d, *tensors):
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
 
 
-def _conv_halo(d, x, w, out, bias=None, out_stats=None):
+def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None):
     """One halo-tile launch; x: tensor or _Pending (normalised on load)."""
     lib = _b200.lib()
     pend = isinstance(x, _Pending)
@@ -261,8 +262,8 @@ def _conv_halo(d, x, w, out, bias=None, out_stats=None):
     nws = int(lib.lsi_b200_conv2d_halo_workspace_bytes(d))
     ws = _tc_workspace(xin.device, nws)
     _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(xin), _b200.ptr(x.stats) if pend else None,
-               _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out), _b200.ptr(out_stats),
-               BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+               _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out_scale), _b200.ptr(out),
+               _b200.ptr(out_stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
 
 
 class _Geometry(object):
@@ -475,12 +476,13 @@ def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False,
 
 
 def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=None, reuse=False, is_training=True,
-                        _scope='pixelwise_pred', _store=None, _out_hw=None):
+                        _scope='pixelwise_pred', _store=None, _out_hw=None, _out_scale=None):
     """nets.py:117-161 -- per layer its own decoder_simple, then a 3x3 conv + bias + sigmoid.  Returns
     (preds [L,B,H,W,nc], end_points)."""
     _require_training(is_training)
     store = _store or get_default_store()
     preds = []
+    packed = None         # inference path: every head writes its slice of one [L,B,H,W,nc] tensor (no tf.stack copy)
     for l in range(n_layers):
         base = '%s/upsample_%d' % (_scope, l)
         # _defer: inside this function nothing but the next conv sees the decoder features, so (inference path) their
@@ -493,23 +495,36 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
         b = store.get('%s/pred_%d/biases' % (base, l), [nc], reuse, 'biases')
         dp = _b200.ConvDesc(**dict(geo.fwd, epilogue=2))
         if _halo_ok(dp, feat_l.z if isinstance(feat_l, _Pending) else feat_l):
-            y = torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
-            _conv_halo(dp, feat_l, w, y, bias=b)
+            if packed is None and l == 0:
+                packed = torch.empty(n_layers, B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
+            y = packed[l] if packed is not None else torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
+            _conv_halo(dp, feat_l, w, y, bias=b, out_scale=_out_scale)
             preds.append(y)
         else:
-            preds.append(_ConvBiasSigmoid.apply(_materialize(feat_l), w, b, geo))
+            y = _ConvBiasSigmoid.apply(_materialize(feat_l), w, b, geo)
+            preds.append(y if _out_scale is None else y * _out_scale)
+    if packed is not None and len(preds) == n_layers and all(p_.data_ptr() == packed[i].data_ptr() for i, p_ in enumerate(preds)):
+        return packed, {}
     return torch.stack(preds, dim=0), {}
 
 
 def ldi_predictor(feat, n_layers=1, reuse=False, n_layerwise_steps=0, skip_feat=None, pred_masks=False, is_training=True,
-                  _store=None, _out_hw=None):
+                  _store=None, _out_hw=None, _disp_scale=None):
     """nets.py:164-208.  Returns ldi = [textures [L,B,H,W,3], masks [L,B,H,W,1], disps [L,B,H,W,1]].  The textures and
     disparities are channel views of the packed [L,B,H,W,nc] head output (no copy); with pred_masks=False the masks
     are all ones and tagged so (the renderer and the losses then never read them)."""
     nc = 3 + 1 + (1 if pred_masks else 0)
+    # _disp_scale (inference, no predicted masks): `disps *= max_disp` (ldi_enc_dec.py:213) as a per-channel output factor
+    # (1, 1, 1, max_disp) of the prediction conv instead of a separate pass over the packed head output
+    out_scale = None
+    if _disp_scale is not None and not pred_masks and not torch.is_grad_enabled():
+        key = (str(feat.device), float(_disp_scale))
+        if key not in _OUT_SCALE_CACHE:           # created once: a per-call host->device copy would stall the launch queue
+            _OUT_SCALE_CACHE[key] = torch.tensor([1.0, 1.0, 1.0, float(_disp_scale)], dtype=torch.float32, device=feat.device)
+        out_scale = _OUT_SCALE_CACHE[key]
     pred, _ = pixelwise_predictor(feat, nc=nc, n_layers=n_layers, n_layerwise_steps=n_layerwise_steps, skip_feat=skip_feat,
                                   reuse=reuse, is_training=is_training, _scope='ldi_tex_disp/pixelwise_pred', _store=_store,
-                                  _out_hw=_out_hw)
+                                  _out_hw=_out_hw, _out_scale=out_scale)
     if pred_masks:
         tex, masks, disps = pred[..., 0:3], pred[..., 3:4], pred[..., 4:5]
         masks = nn_helpers.enforce_bg_occupied(torch.sigmoid(masks))      # sigmoid applied twice, as nets.py:143,202

@@ -65,14 +65,18 @@ def predict_ldi(img, opts, store, reuse):
     _, feat_dec, skip_feat, _ = nets.encoder_decoder_unet(padded, nl_diff_enc_dec=opts.n_layerwise_steps, reuse=reuse,
                                                           _store=store)
     # the crop back to (h, w) is fused into the prediction conv (it only evaluates the top-left window)
+    if not torch.is_grad_enabled() and not opts.pred_ldi_masks:
+        # inference: the disparity scale is a per-channel output factor of the prediction conv, so textures and
+        # disparities stay views of ONE packed [L,B,H,W,4] tensor and the renderer reads 16 bytes per pixel-layer
+        return nets.ldi_predictor(feat_dec, n_layers=opts.n_layers, reuse=reuse, n_layerwise_steps=opts.n_layerwise_steps,
+                                  skip_feat=skip_feat, pred_masks=False, _store=store, _out_hw=(h, w),
+                                  _disp_scale=(None if opts.max_disp == 1 else opts.max_disp))
     tex, masks, disps = nets.ldi_predictor(feat_dec, n_layers=opts.n_layers, reuse=reuse,
                                            n_layerwise_steps=opts.n_layerwise_steps, skip_feat=skip_feat,
                                            pred_masks=opts.pred_ldi_masks, _store=store, _out_hw=(h, w))
     if opts.max_disp == 1:
         return [tex, masks, disps]
     if not torch.is_grad_enabled():
-        # inference: scale the disparity channel of the packed [L,B,H,W,4] head output in place, so that textures and
-        # disparities stay views of one packed tensor and the renderer reads 16 bytes per pixel-layer
         disps.mul_(opts.max_disp)
         return [tex, masks, disps]
     return [tex, masks, disps * opts.max_disp]

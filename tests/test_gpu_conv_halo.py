@@ -49,7 +49,7 @@ def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=Non
     nws = lib.lsi_b200_conv2d_halo_workspace_bytes(d)
     wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
     _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w), _b200.ptr(bias),
-               _b200.ptr(out), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
+               None, _b200.ptr(out), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
     torch.cuda.synchronize()
     return out, ref, st
 
@@ -134,5 +134,5 @@ def test_unsupported_shapes_are_refused():
     d = _b200.ConvDesc(**dict(base, c_out=128, out_c_stride=128))
     x = torch.zeros(1, 16, 16, 32, device='cuda')
     with pytest.raises(RuntimeError):
-        _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), None, None, _b200.ptr(x), None, _b200.ptr(x), None, EPS,
+        _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), None, None, _b200.ptr(x), None, None, _b200.ptr(x), None, EPS,
                    _b200.ptr(x), 4, _b200.stream())

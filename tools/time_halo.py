@@ -41,7 +41,7 @@ for name, kw, has_stats in layers:
 
     def run():
         _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w), _b200.ptr(bias),
-                   _b200.ptr(out), _b200.ptr(st), 1e-3, _b200.ptr(ws), nws, _b200.stream())
+                   None, _b200.ptr(out), _b200.ptr(st), 1e-3, _b200.ptr(ws), nws, _b200.stream())
     for _ in range(3):
         run()
     torch.cuda.synchronize()
