@@ -266,7 +266,7 @@ def main():
     wp = -(-W // 128) * 128
     conv_flops = (21.8e9 + 23.0e9 * L) * (H * wp) / (256.0 * 768.0) * B      # forward 2*MAC per step
     conv_ms = (kms[4] + kms[5]) / args.steps
-    conv = {'bound': 'tensor', 'kernel': 'conv_tc_kernel (tcgen05 TF32) + fp32 stem', 'achieved': conv_flops / (conv_ms * 1e-3) / 1e12,
+    conv = {'bound': 'tensor', 'kernel': 'conv_tc_kernel + conv_halo_kernel (tcgen05 TF32, TMA) + fp32 stem', 'achieved': conv_flops / (conv_ms * 1e-3) / 1e12,
             'unit': 'TFLOP/s', 'kernel_ms_per_step': conv_ms, 'tc_ms_per_step': kms[4] / args.steps,
             'fp32_ms_per_step': kms[5] / args.steps, 'flops_per_step': conv_flops,
             'share_of_step': conv_ms / ms_per_step, 'note': 'TF32 dense peak is ~half of the measured bf16 peak in MEASURED_PEAKS.json'}
@@ -287,6 +287,33 @@ def main():
     torch.cuda.synchronize()
     renderer_only = B / (r0.elapsed_time(r1) / 20 * 1e-3)
     del ldi_fixed
+
+    # --- the same kernel on SURVEY.md 8(d)'s structured config-4 LDI (road-plane disparity ramps + smooth bumps, what a
+    #     trained network predicts).  The random-init CNN above emits checkerboard noise from its untrained 4x4/2
+    #     up-convolutions (neighbouring disparities differ by ~20 target pixels), i.e. a fully scattered splat. -----------
+    s_tex = torch.tensor(host['tex'], device=dev)
+    s_disp = torch.tensor(host['disp'], device=dev)
+    s_mask = torch.ones(L, B, H, W, 1, device=dev)
+    s_mask._lsi_all_ones = True
+    for _ in range(3):
+        with torch.no_grad():
+            ldi_utils.forward_splat((s_tex, s_mask, s_disp), pc, *cam, **kw)
+    torch.cuda.synchronize()
+    lib.lsi_b200_kernel_timing_enable(1)
+    for _ in range(10):
+        with torch.no_grad():
+            ldi_utils.forward_splat((s_tex, s_mask, s_disp), pc, *cam, **kw)
+    torch.cuda.synchronize()
+    kms2, kn2 = (ctypes.c_double * 8)(), (ctypes.c_int * 8)()
+    _b200.call('lsi_b200_kernel_timing_collect', ctypes.cast(kms2, ctypes.c_void_p), ctypes.cast(kn2, ctypes.c_void_p))
+    lib.lsi_b200_kernel_timing_enable(0)
+    s_ms = kms2[0] / 10
+    s_ach = splat_bytes_per_step / (s_ms * 1e-3) / 1e9
+    roofline['structured_ldi'] = {'what': 'same kernel, same shapes, SURVEY.md 8(d) config-4 synthetic LDI (planar tex [.,3] + disp [.,1] '
+                                          'tensors: 16 B per pixel-layer) instead of the random-init CNN output',
+                                  'achieved': s_ach, 'frac': s_ach / peak, 'kernel_ms_per_step': s_ms,
+                                  'normalize_ms_per_step': kms2[1] / 10}
+    del s_tex, s_disp, s_mask
 
     # --- end to end through the public API with HOST buffers: every step copies its images + cameras host->device and its
     #     rendered views device->host (train_utils.HostViewPipeline: the copies of neighbouring steps overlap the kernels) ----
