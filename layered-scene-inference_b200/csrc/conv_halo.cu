@@ -18,6 +18,7 @@
 //   pipeline     persistent CTAs; warp 0 TMA producer, warp 1 single-thread MMA issuer (double-buffered TMEM
 //                accumulators), warps 2-5 epilogue, warps 6-9 transform; mbarrier ring over tiles.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "capi_common.h"
 #include "common.cuh"
@@ -28,7 +29,8 @@ namespace {
 constexpr int kTH = 16, kTW = 8, kTileM = kTH * kTW;   // 128 output pixels = 128 TMEM lanes
 constexpr int kKC = 32;                                // fp32 channels per 128-byte row
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 320;
+constexpr int kThreads = 320;                          // warp 0 TMA, 1 MMA, 2-5 epilogue, 6-9 transform
+constexpr int kThreadsWide = 448;                      // 1-CTA/SM variant: 8 transform warps (6-13)
 constexpr int kStgPitch = 36;                          // floats per staged pixel (144 B: conflict-free 128-bit rows)
 constexpr int kMaxCin = 128;
 
@@ -40,6 +42,7 @@ struct HaloParams {
   int tiles_x, per_img, spatial_tiles;
   int chunks, kh, kw, stride, pad_t, pad_l, mode;
   int n_tile, epilogue, stages;
+  int f16;                   // 1: transform warps also convert the normalised tile to fp16 in place; MMAs run kind::f16
   int halo_w, halo_h;
   uint32_t halo_bytes, b_tap_bytes, w_bytes, div_halo_w;
 };
@@ -88,6 +91,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile with the 64-byte swizzle (fp16 weights: 32 channels = 64-byte rows), 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_hi_sw64() {
+  return ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -128,7 +143,67 @@ struct TileIter {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// One halo tile (halo_w * halo_h pixel rows of 128 bytes = 32 fp32 channels, 128B-swizzled as TMA wrote it), 128 threads:
+// y = max(x * a + b, 0) for pixels inside the image, 0 outside (SAME padding of the NORMALISED tensor).
+// thread -> (16-byte column j, pixels p0, p0 + kNT/8, ...): the pixel step is a multiple of 8, so the swizzle phase -- hence the four
+// channels this thread touches -- is fixed and scale/shift live in registers.
+// kF16: additionally convert to fp16 IN PLACE: row p keeps its 128-byte pitch, its 32 channels become four 16-byte chunks
+// at swizzled positions (c ^ (p & 7)), i.e. the K-major SWIZZLE_128B layout of a 64-channel-wide fp16 tile of which the MMA
+// reads K = 0..31.  The two lanes that hold fp32 chunks 2c and 2c+1 of a row are neighbours (j and j ^ 1): one shuffle
+// pairs them, the even one stores.  All 8 lanes of a row belong to one warp instruction, so every read of a row precedes
+// every write to it.
+template <bool kF16, bool kInterior, int kNT>
+__device__ __forceinline__ void transform_tile(float4* tile, const float* bn_a, const float* bn_b, int tid, const HaloParams& p,
+                                               int ys0, int xs0) {
+  const int j = tid & 7, p0 = tid >> 3, s7 = p0 & 7;
+  const int jl = j ^ s7;                                     // logical 16-byte fp32 chunk = channels 4*jl .. 4*jl+3
+  const float4 a = *reinterpret_cast<const float4*>(bn_a + (jl << 2));
+  const float4 b = *reinterpret_cast<const float4*>(bn_b + (jl << 2));
+  const int npx = p.halo_w * p.halo_h;
+  constexpr int kRows = kNT / 8;                             // pixel rows covered per pass (16 with 128 threads, 32 with 256)
+  const int iters = (npx + kRows - 1) / kRows;               // warp-uniform trip count (shuffles below)
+  float4* q = tile + tid;                                    // item k lives at q + kNT * k
+  const int wr = ((jl >> 1) ^ s7) - j;                       // fp16 mode: float4 offset of this pair's output chunk from q
+  for (int k0 = 0; k0 < iters; k0 += 4) {
+    float4 v[4]; bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pxl = p0 + kRows * (k0 + u);
+      ok[u] = pxl < npx;
+      v[u] = ok[u] ? q[kNT * (k0 + u)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      bool inb = ok[u];
+      if (!kInterior) {
+        const int pxl = p0 + kRows * (k0 + u);
+        const int hy = (int)(((uint32_t)pxl * p.div_halo_w) >> 16), hx = pxl - hy * p.halo_w;
+        inb = inb && (unsigned)(ys0 + hy) < (unsigned)p.Hin && (unsigned)(xs0 + hx) < (unsigned)p.Win;
+      }
+      float4 y;
+      y.x = inb ? fmaxf(fmaf(v[u].x, a.x, b.x), 0.f) : 0.f; y.y = inb ? fmaxf(fmaf(v[u].y, a.y, b.y), 0.f) : 0.f;
+      y.z = inb ? fmaxf(fmaf(v[u].z, a.z, b.z), 0.f) : 0.f; y.w = inb ? fmaxf(fmaf(v[u].w, a.w, b.w), 0.f) : 0.f;
+      if (kF16) {
+        const uint32_t h01 = pack_half2(y.x, y.y), h23 = pack_half2(y.z, y.w);
+        const uint32_t o01 = __shfl_xor_sync(0xffffffffu, h01, 1), o23 = __shfl_xor_sync(0xffffffffu, h23, 1);
+        if (ok[u] && !(jl & 1))
+          *reinterpret_cast<uint4*>(q + kNT * (k0 + u) + wr) = make_uint4(h01, h23, o01, o23);
+      } else {
+        if (ok[u]) q[kNT * (k0 + u)] = y;
+      }
+    }
+  }
+}
+
+// kWide: n_tile == 64 (two 32-column passes per accumulator, two sets of statistics registers)
+template <bool kWide>
+__global__ void __launch_bounds__(kWide ? kThreadsWide : kThreads, kWide ? 1 : 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
@@ -169,7 +244,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&xready[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&xready[i], kWide ? 8 : 4); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -179,7 +254,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (bn_in) {   // y = max(x * a + b, 0) with a = rstd, b = beta - mean * rstd
-    for (int c = threadIdx.x; c < p.chunks * kKC; c += kThreads) {
+    for (int c = threadIdx.x; c < p.chunks * kKC; c += blockDim.x) {
       const float mean = __ldg(p.in_stats + 2 * c), rstd = __ldg(p.in_stats + 2 * c + 1);
       bn_a[c] = rstd; bn_b[c] = fmaf(-mean, rstd, __ldg(p.in_beta + c));
     }
@@ -192,7 +267,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       // ---------------- TMA producer ----------------
-      mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)p.n_tile * 128u);
+      mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)p.n_tile * (p.f16 ? 64u : 128u));
       for (int i = 0; i < nky; ++i)
         for (int j = 0; j < nkx; ++j)
           for (int ch = 0; ch < p.chunks; ++ch)
@@ -214,8 +289,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (elect_one()) {
       // ---------------- MMA issuer ----------------
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint64_t hi_a = umma_desc_hi((uint32_t)p.halo_w * 128u), hi_b = umma_desc_hi(1024u);
+      // (kind::f16: A/B format F16 = 0, two K = 16 steps per 32-channel chunk)
+      const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
+                                   : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
+      const uint64_t hi_a = umma_desc_hi((uint32_t)p.halo_w * 128u), hi_b = p.f16 ? umma_desc_hi_sw64() : umma_desc_hi(1024u);
       mbar_wait(wfull, 0);
       const uint64_t b_desc0 = umma_desc(hi_b, smem_u32(s_w));
       Ring r(p.stages);
@@ -237,10 +314,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               const int dx = (p.mode == 0) ? j : nkx - 1 - j;
               const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * 128u) >> 4);
               const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes) >> 4);
+              if (p.f16) {
 #pragma unroll
-              for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
-                umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
-                acc = 1;
+                for (int kk = 0; kk < kKC / 16; ++kk) {  // UMMA K = 16 for fp16: 32 bytes along the row
+                  umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                  acc = 1;
+                }
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+                  umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                  acc = 1;
+                }
               }
             }
           }
@@ -255,7 +340,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int row = lg * 32 + lane;              // A-tile row = pixel within the 16 x 8 patch
     const int hy = row >> 3, wx = row & 7;
     float* stg = staging + (size_t)lg * 32 * kStgPitch;
-    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};   // channel (32 * i + lane) sums over this warp's pixels
+    // batch statistics: lane (q4, c4) meets channels cc + c4 .. c4 + 3 of pixels q4, q4 + 4, ... in the store loop below and
+    // sums them there (zero rows for pixels outside the output), so the statistics cost no extra shared-memory reads
+    float4 ssum0 = make_float4(0.f, 0.f, 0.f, 0.f), ssum1 = ssum0, ssq0 = ssum0, ssq1 = ssum0;   // channels cc = 0 / cc = 32
     const bool direct4 = (p.Co <= 4 && p.out_cs == 4);   // prediction head: one 16-byte store per pixel
     int tcount = 0;
     TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
@@ -265,7 +352,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool in_range = (y0 + hy) < p.Hp && (x0 + wx) < p.Wp;
-      for (int cc = 0; cc < p.n_tile; cc += 32) {
+      for (int cc = 0; cc < (kWide ? 64 : p.n_tile); cc += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc;
         if (p.n_tile - cc >= 32) {
@@ -325,41 +412,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           *reinterpret_cast<float4*>(stg + lane * kStgPitch + j) = v;
         }
         __syncwarp();
-        if (p.stat_part) {
-          float a = 0.f, b2 = 0.f;
-#pragma unroll 8
-          for (int q = 0; q < 32; ++q) { const float v = stg[q * kStgPitch + lane]; a += v; b2 = fmaf(v, v, b2); }
-          ssum[cc >> 5] += a; ssq[cc >> 5] += b2;
-        }
         // coalesced stores: each instruction writes 4 pixels x 128 bytes
         const int q4 = lane >> 3, c4 = (lane & 7) * 4;
+        float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sq = sa;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int pxi = i * 4 + q4;
           int oy = y0 + lg * 4 + (pxi >> 3), ox = x0 + (pxi & 7);
+          const float4 v = *reinterpret_cast<const float4*>(stg + pxi * kStgPitch + c4);
+          sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
+          sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
           if (oy < p.Hp && ox < p.Wp) {
             if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
-            const float4 v = *reinterpret_cast<const float4*>(stg + pxi * kStgPitch + c4);
             *reinterpret_cast<float4*>(p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4) = v;
           }
+        }
+        if (cc == 0) {
+          ssum0.x += sa.x; ssum0.y += sa.y; ssum0.z += sa.z; ssum0.w += sa.w;
+          ssq0.x += sq.x; ssq0.y += sq.y; ssq0.z += sq.z; ssq0.w += sq.w;
+        } else if (kWide) {
+          ssum1.x += sa.x; ssum1.y += sa.y; ssum1.z += sa.z; ssum1.w += sa.w;
+          ssq1.x += sq.x; ssq1.y += sq.y; ssq1.z += sq.z; ssq1.w += sq.w;
         }
       }
     }
     if (p.stat_part) {
       float* my_part = p.stat_part + ((size_t)blockIdx.x * 4 + lg) * p.n_tile * 2;
-      for (int i = 0; i < 2; ++i) {
-        const int ch = 32 * i + lane;
-        if (ch < p.n_tile) { my_part[2 * ch] = ssum[i]; my_part[2 * ch + 1] = ssq[i]; }
+#pragma unroll
+      for (int i = 0; i < (kWide ? 2 : 1); ++i) {
+        const float4 fs = i ? ssum1 : ssum0, fq = i ? ssq1 : ssq0;
+        float v[8] = {fs.x, fs.y, fs.z, fs.w, fq.x, fq.y, fq.z, fq.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {       // lanes that share c4 (q4 = 0..3) hold partial sums of the same channels
+          v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+          v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+        }
+        const int ch = 32 * i + (lane & 7) * 4;
+        if (lane < 8 && ch < p.n_tile) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { my_part[2 * (ch + k)] = v[k]; my_part[2 * (ch + k) + 1] = v[4 + k]; }
+        }
       }
     }
   } else if (bn_in) {
     // ---------------- transform: producer's batch-norm + ReLU applied to the halo tile in shared memory ----------------
-    // thread -> (16-byte column j, pixels p0, p0+16, ...): (p0 + 16k) & 7 == p0 & 7, so the 128B-swizzle phase, hence the
-    // four channels this thread touches, are fixed: scale/shift live in registers, the loop is LDS.128 / 8 flops / STS.128
     const int tid = threadIdx.x - 192;
-    const int j = tid & 7, p0 = tid >> 3;
-    const int cgrp = (j ^ (p0 & 7)) << 2;
-    const int npx = p.halo_w * p.halo_h;
     Ring r(p.stages);
     TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
     for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ti.next()) {
@@ -367,35 +464,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool interior = ys0 >= 0 && xs0 >= 0 && ys0 + p.halo_h <= p.Hin && xs0 + p.halo_w <= p.Win;
       for (int ch = 0; ch < p.chunks; ++ch, r.next()) {
         mbar_wait(&full[r.st], r.ph);
-        const float4 a = *reinterpret_cast<const float4*>(bn_a + ch * kKC + cgrp);
-        const float4 b = *reinterpret_cast<const float4*>(bn_b + ch * kKC + cgrp);
-        float4* q = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes) + tid;
-        if (interior) {
-          int pxl = p0;
-          for (; pxl + 48 < npx; pxl += 64, q += 512) {     // 4 independent items in flight
-            float4 v0 = q[0], v1 = q[128], v2 = q[256], v3 = q[384];
-            v0.x = fmaxf(fmaf(v0.x, a.x, b.x), 0.f); v0.y = fmaxf(fmaf(v0.y, a.y, b.y), 0.f); v0.z = fmaxf(fmaf(v0.z, a.z, b.z), 0.f); v0.w = fmaxf(fmaf(v0.w, a.w, b.w), 0.f);
-            v1.x = fmaxf(fmaf(v1.x, a.x, b.x), 0.f); v1.y = fmaxf(fmaf(v1.y, a.y, b.y), 0.f); v1.z = fmaxf(fmaf(v1.z, a.z, b.z), 0.f); v1.w = fmaxf(fmaf(v1.w, a.w, b.w), 0.f);
-            v2.x = fmaxf(fmaf(v2.x, a.x, b.x), 0.f); v2.y = fmaxf(fmaf(v2.y, a.y, b.y), 0.f); v2.z = fmaxf(fmaf(v2.z, a.z, b.z), 0.f); v2.w = fmaxf(fmaf(v2.w, a.w, b.w), 0.f);
-            v3.x = fmaxf(fmaf(v3.x, a.x, b.x), 0.f); v3.y = fmaxf(fmaf(v3.y, a.y, b.y), 0.f); v3.z = fmaxf(fmaf(v3.z, a.z, b.z), 0.f); v3.w = fmaxf(fmaf(v3.w, a.w, b.w), 0.f);
-            q[0] = v0; q[128] = v1; q[256] = v2; q[384] = v3;
-          }
-          for (; pxl < npx; pxl += 16, q += 128) {
-            float4 v = *q;
-            v.x = fmaxf(fmaf(v.x, a.x, b.x), 0.f); v.y = fmaxf(fmaf(v.y, a.y, b.y), 0.f);
-            v.z = fmaxf(fmaf(v.z, a.z, b.z), 0.f); v.w = fmaxf(fmaf(v.w, a.w, b.w), 0.f);
-            *q = v;
-          }
-        } else {     // image border: pixels outside the input stay zero (SAME padding of the NORMALISED tensor)
-          for (int pxl = p0; pxl < npx; pxl += 16, q += 128) {
-            const int hy = (int)(((uint32_t)pxl * p.div_halo_w) >> 16), hx = pxl - hy * p.halo_w;
-            if ((unsigned)(ys0 + hy) < (unsigned)p.Hin && (unsigned)(xs0 + hx) < (unsigned)p.Win) {
-              float4 v = *q;
-              v.x = fmaxf(fmaf(v.x, a.x, b.x), 0.f); v.y = fmaxf(fmaf(v.y, a.y, b.y), 0.f);
-              v.z = fmaxf(fmaf(v.z, a.z, b.z), 0.f); v.w = fmaxf(fmaf(v.w, a.w, b.w), 0.f);
-              *q = v;
-            }
-          }
+        float4* tile = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes);
+        const float* ta = bn_a + ch * kKC; const float* tb = bn_b + ch * kKC;
+        constexpr int kNT = kWide ? 256 : 128;
+        if (p.f16) {
+          if (interior) transform_tile<true, true, kNT>(tile, ta, tb, tid, p, ys0, xs0);
+          else transform_tile<true, false, kNT>(tile, ta, tb, tid, p, ys0, xs0);
+        } else {
+          if (interior) transform_tile<false, true, kNT>(tile, ta, tb, tid, p, ys0, xs0);
+          else transform_tile<false, false, kNT>(tile, ta, tb, tid, p, ys0, xs0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         __syncwarp();
@@ -419,6 +496,18 @@ __global__ void __launch_bounds__(256) halo_prep_weights_kernel(const float* __r
     const int co = (int)((i / cin) % n_pad);
     const int tap = (int)(i / ((long long)cin * n_pad));
     wk[i] = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+  }
+}
+
+// same, rounded to fp16 (the operand type of the kind::f16 path)
+__global__ void __launch_bounds__(256) halo_prep_weights_f16_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
+                                                                    int cout, int n_pad, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * n_pad * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % n_pad);
+    const int tap = (int)(i / ((long long)cin * n_pad));
+    wk[i] = __float2half_rn((co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f);
   }
 }
 
@@ -469,7 +558,7 @@ struct HaloPlan {
   size_t smem;
 };
 
-bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl) {
+bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false) {
   if (!d) return false;
   if (d->c_in % kKC != 0 || d->c_in > kMaxCin || d->c_in < kKC) return false;
   if (d->mode != 0 && d->mode != 1) return false;
@@ -486,7 +575,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl) {
   if (pl->nky_max * pl->nkx_max > 9) return false;
   pl->halo_w = kTW + pl->nkx_max - 1; pl->halo_h = kTH + pl->nky_max - 1;
   pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * 128u + 1023u) & ~1023u;
-  pl->b_tap_bytes = ((uint32_t)pl->n_tile * 128u + 1023u) & ~1023u;
+  pl->b_tap_bytes = ((uint32_t)pl->n_tile * (f16 ? 64u : 128u) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows
   pl->w_bytes = (uint32_t)(pl->nky_max * pl->nkx_max * pl->chunks) * pl->b_tap_bytes;
   const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + 4 * 32 * kStgPitch * sizeof(float);
   const size_t stage = (size_t)pl->halo_bytes;   // one 32-channel chunk of one tile's halo
@@ -494,7 +583,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl) {
   static int force_ctas = -1, max_stages = -1;   // measurement knobs
   if (force_ctas < 0) { const char* e = getenv("LSI_B200_HALO_CTAS"); force_ctas = e ? atoi(e) : 0; }
   if (max_stages < 0) { const char* e = getenv("LSI_B200_HALO_STAGES"); max_stages = e ? atoi(e) : 0; }
-  if (force_ctas != 1 && fixed + 2 * stage <= budget2) {
+  if (force_ctas != 1 && pl->n_tile <= 32 && fixed + 2 * stage <= budget2) {   // the 64-column variant is built for 1 CTA/SM
     pl->ctas_per_sm = 2;
     pl->stages = (int)((budget2 - fixed) / stage);
   } else if (fixed + 2 * stage <= budget1) {
@@ -534,6 +623,13 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   HaloPlan pl;
   LSI_REQUIRE(halo_plan(d, &pl), "shape not supported by the halo-tile tensor-core path");
   LSI_REQUIRE((in_bn_stats == nullptr) == (in_bn_beta == nullptr), "in_bn_stats and in_bn_beta go together");
+  // fp16 operands (same 10-bit mantissa as TF32, fp32 accumulation) whenever the transform warps rewrite the tile anyway:
+  // normalised post-ReLU activations are O(1), far inside fp16's range; halves the operand bytes the MMAs pull from
+  // shared memory, the resource these layers are bound by
+  static int f16_on = -1;
+  if (f16_on < 0) { const char* e = getenv("LSI_B200_HALO_F16"); f16_on = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool f16 = in_bn_stats != nullptr && f16_on == 1;
+  if (f16) { LSI_REQUIRE(halo_plan(d, &pl, true), "halo plan (fp16) failed"); }
   LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
   LSI_REQUIRE(!out_bn_stats || (d->epilogue == 0 && pl.n_tile == d->c_out), "bn statistics need a plain 32/64-channel conv output");
   LSI_REQUIRE(workspace_bytes >= lsi_b200_conv2d_halo_workspace_bytes(d), "workspace too small");
@@ -553,7 +649,7 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   const int tiles_y = (p.Hp + kTH - 1) / kTH;
   p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
   p.chunks = pl.chunks; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
-  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages;
+  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0;
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
   p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
 
@@ -563,8 +659,12 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   {
     const long long total = (long long)taps * pl.n_tile * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    halo_prep_weights_kernel<<<(unsigned)g, 256, 0, st>>>(w, wk, taps, d->c_in, d->c_out, pl.n_tile, d->w_tap_stride, d->w_ci_stride,
-                                                          d->w_co_stride);
+    if (f16)
+      halo_prep_weights_f16_kernel<<<(unsigned)g, 256, 0, st>>>(w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, pl.n_tile,
+                                                                d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
+    else
+      halo_prep_weights_kernel<<<(unsigned)g, 256, 0, st>>>(w, wk, taps, d->c_in, d->c_out, pl.n_tile, d->w_tap_stride, d->w_ci_stride,
+                                                            d->w_co_stride);
     LSI_LAUNCH_CHECK();
   }
   CUtensorMap map_a, map_w;
@@ -581,17 +681,20 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * pl.n_tile};
-    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * (f16 ? 2 : 4)};
     cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)pl.n_tile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(&map_w, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
-  static size_t smem_set = 0;
-  if (pl.smem > smem_set) {
-    LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    smem_set = pl.smem;
+  const bool wide = pl.n_tile > 32;
+  static size_t smem_set[2] = {0, 0};
+  if (pl.smem > smem_set[wide]) {
+    if (wide) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    smem_set[wide] = pl.smem;
   }
   const int G = s * s;
   int n_ctas = halo_num_sms() * pl.ctas_per_sm;
@@ -604,7 +707,8 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   }
   {
     ScopedTiming tm(kConvTc, st);
-    conv_halo_kernel<<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_w, p);
+    if (wide) conv_halo_kernel<true><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_w, p);
+    else conv_halo_kernel<false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_w, p);
   }
   LSI_LAUNCH_CHECK();
   if (out_bn_stats) {
