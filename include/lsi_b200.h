@@ -65,7 +65,9 @@ typedef struct lsi_b200_splat_desc {
    * output (nets.py:204).  (layer,batch) images must be densely packed: image stride = h_s*w_s*px_stride. */
   int tex_px_stride, disp_px_stride, mask_px_stride;
   int variant;                                 /* 0 = default; 1 = plain global-atomic kernel (ablation);   */
-                                               /* 2 = deterministic row-owner kernel for rectified poses     */
+                                               /* 2 = deterministic row-owner kernel for rectified poses;    */
+                                               /* 3 = block-per-segment reduction kernel without the bulk-   */
+                                               /* copy ring (the default before the streaming kernel)        */
 } lsi_b200_splat_desc;
 
 /* src->trg (inverse==0, projection.py:71-86) or trg->src (inverse!=0, projection.py:89-106) 4x4 matrices.

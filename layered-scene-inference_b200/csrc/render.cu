@@ -9,6 +9,7 @@
 #include "capi_common.h"
 #include "common.cuh"
 #include "render_fast.cuh"
+#include "render_stream.cuh"
 #include "render_rowowner.cuh"
 
 namespace lsi {
@@ -317,7 +318,7 @@ static int chunk_budget_mb() {
   static int mb = -1;
   if (mb < 0) {
     const char* e = getenv("LSI_B200_CHUNK_MB");
-    mb = e ? atoi(e) : 48;
+    mb = e ? atoi(e) : 64;
     if (mb < 1) mb = 1;
   }
   return mb;
@@ -334,10 +335,15 @@ static FwdPlan plan_forward(const lsi_b200_splat_desc* d) {
   if (bc < 1) bc = 1;
   if (bc > (size_t)d->batch) bc = d->batch;
   if (bc > 65535) bc = 65535;
+  const size_t n_chunks = ((size_t)d->batch + bc - 1) / bc;   // equal chunks: no short last launch
+  bc = ((size_t)d->batch + n_chunks - 1) / n_chunks;
   pl.bc = (int)bc;
   pl.off_mats = 0;
-  pl.off_acc4 = align_up((size_t)d->batch * 17 * sizeof(float), 256);   // matrices + rectified-class flags
-  pl.off_accd = pl.off_acc4 + align_up(n_trg * 16 * pl.nl_acc * bc, 256);
+  // guard band on both sides of the chunk accumulator: the streaming kernel adds exact zeros to the (clamped) cell of a
+  // pixel that projects outside the image instead of branching around the reduction (render_stream.cuh)
+  const size_t guard = align_up(((size_t)4 * d->w_t + 8) * 16, 256);
+  pl.off_acc4 = align_up((size_t)d->batch * 17 * sizeof(float), 256) + guard;   // matrices + rectified-class flags
+  pl.off_accd = pl.off_acc4 + align_up(n_trg * 16 * pl.nl_acc * bc, 256) + guard;
   pl.total = pl.off_accd + (d->compute_trg_disp ? align_up(n_trg * 8 * d->n_layers * bc, 256) : 0);
   return pl;
 }
@@ -386,6 +392,60 @@ static float bg_weight(const lsi_b200_splat_desc* d) {
   float r = d->bg_layer_disp / d->max_disp;
   float c = fminf(fmaxf(r, 0.f), 1.f);
   return r > 0.f ? expf((c - 0.5f) * d->zbuf_scale) : 0.f;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static bool stream_enabled() {
+  static int on = -1;
+  if (on < 0) on = env_int("LSI_B200_SPLAT_STREAM", 1) != 0 ? 1 : 0;
+  return on == 1;
+}
+
+// Persistent streaming splat (render_stream.cuh): grid = SMs x resident CTAs, each warp a contiguous unit range.
+static int launch_stream(const FastParams& f, bool has_mask, bool packed, cudaStream_t st) {
+  static int sms = 0, stages = 0, ctas_env = -1;
+  if (!sms) {
+    int dev = 0;
+    LSI_CUDA(cudaGetDevice(&dev));
+    LSI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    stages = env_int("LSI_B200_STREAM_STAGES", kStreamQuad ? 3 : 2);
+    if (stages < 2) stages = 2;
+    if (stages > 4) stages = 4;
+    ctas_env = env_int("LSI_B200_STREAM_CTAS", 0);
+  }
+  StreamParams p;
+  p.f = f;
+  p.segs = (f.W + kSegPx - 1) / kSegPx;
+  p.groups = (f.L + 3) / 4;
+  p.stages = stages;
+  p.stage_bytes = 4 * kSegPx * 16 + (has_mask ? 4 * kSegPx * 4 : 0);
+  p.units = (long long)f.bc * f.H * p.segs;
+  LSI_REQUIRE(p.units * p.groups < (1ll << 31), "LDI chunk too large for the streaming splat kernel");
+  const size_t smem = 128 + (size_t)kStreamWarps * stages * p.stage_bytes;
+  int per_sm = (int)(232448 / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (ctas_env > 0 && ctas_env < per_sm) per_sm = ctas_env;
+  long long grid = (long long)sms * per_sm;
+  const long long need = (p.units + kStreamWarps - 1) / kStreamWarps;
+  if (grid > need) grid = need;
+  const int ki = (has_mask ? 2 : 0) | (packed ? 1 : 0);
+  auto kern = ki == 0 ? splat_fwd_stream_kernel<false, false> : ki == 1 ? splat_fwd_stream_kernel<false, true>
+            : ki == 2 ? splat_fwd_stream_kernel<true, false> : splat_fwd_stream_kernel<true, true>;
+  static size_t smem_set[4] = {0, 0, 0, 0};
+  if (smem > smem_set[ki]) {
+    LSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[ki] = smem;
+  }
+  {
+    ScopedTiming tm(kSplatFwd, st);
+    kern<<<(unsigned)grid, kStreamWarps * 32, smem, st>>>(p);
+  }
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
 }
 
 template <typename K, typename P>
@@ -442,13 +502,17 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   // fast path: standard grid, no focal shift, no trg_disp, 16-byte aligned rows, planar (3/1/1) or packed (4/4) layout
   const bool packed = d->tex_px_stride == 4 && d->disp_px_stride == 4 && disp == tex + 3;
   const bool planar = d->tex_px_stride == 3 && d->disp_px_stride == 1;
-  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
+  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant == 3 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
                     (!mask || d->mask_px_stride == 1) && (!packed || ((uintptr_t)tex & 15) == 0) && d->h_s <= 65535 &&
                     bc_fits_grid;
   // rectified-stereo pose class: warp-owned target rows in shared memory, written once (render_rowowner.cuh); images of
   // any other class fall through to the reduction kernels below, which skip the flagged ones
   const int* skip = nullptr;
   const bool fast_eligible = fast;
+  // streaming kernel (render_stream.cuh): bulk copies need 16-byte aligned row segments
+  const bool use_stream = fast && d->variant == 0 && !rowowner_enabled() && stream_enabled() && ((uintptr_t)tex & 15) == 0 &&
+                      (packed || (d->w_s % 4 == 0 && ((uintptr_t)disp & 15) == 0)) &&
+                      (!mask || (d->w_s % 4 == 0 && ((uintptr_t)mask & 15) == 0));
   if (fast_eligible && (d->variant == 2 || rowowner_enabled())) {
     int R = (int)(14336 / ((size_t)d->w_t * 16));
     if (R > 4) R = 4;
@@ -507,7 +571,9 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
       f.ablate = (d->variant >= 100) ? d->variant - 100 : 0;
       f.skip = skip;
       dim3 fgrid((d->w_s + 63) / 64, d->h_s, bc), fblock(64);
-      {
+      if (use_stream) {
+        if (int rc = launch_stream(f, mask != nullptr, packed, st)) return rc;
+      } else {
         ScopedTiming tm(kSplatFwd, st);
         if (packed) {
           if (mask) launch3(splat_fwd_fast_kernel<true, true>, fgrid, fblock, st, f);

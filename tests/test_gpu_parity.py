@@ -3,6 +3,7 @@
 generated from the reference's own sources.  Tolerance: BASELINE.json's "1e-4 relative fp32", measured as
 max|a-b| / max|b| per tensor (rel_err in tests/_util.py)."""
 import ctypes
+import math
 
 import numpy as np
 import pytest
@@ -90,6 +91,13 @@ def test_forward_splat_input_forms_agree(lsi_mods, name):
     alt = ldi.forward_splat((tex, mask, disp), pc, *cam, compute_trg_disp=True, _variant=1, **kw)
     for a, b in zip(ref, alt):
         assert rel_err(a.cpu(), b.cpu()) < 1e-5
+    # streaming kernel (default) vs the ring-less reduction kernel (variant 3) vs the plain atomic kernel
+    for compose in (True, False):
+        base = ldi.forward_splat((tex, mask, disp), pc, *cam, compose_layers=compose, **kw)
+        for v in (1, 3):
+            alt = ldi.forward_splat((tex, mask, disp), pc, *cam, compose_layers=compose, _variant=v, **kw)
+            for a, b in zip(base, alt):
+                assert rel_err(a.cpu(), b.cpu()) < 1e-5
     # deterministic row-owner kernel (rectified poses; other poses fall through to the reduction kernels), both
     # compose modes; run twice: bitwise reproducible
     for compose in (True, False):
@@ -300,3 +308,35 @@ def test_error_behaviour(lsi_mods):
     desc = b200.SplatDesc(1, 1, 8, 8, 8, 8, 1.0, 0.0, 0.0, 10.0, 1, 0, 3, 1, 1, 0)   # max_disp == 0
     assert b200.lib().lsi_b200_forward_splat_workspace_bytes(desc) == 0
     assert b'max_disp' in b200.lib().lsi_b200_last_error()
+
+
+@pytest.mark.parametrize('W,L,packed,with_mask', [(70, 5, True, False), (64, 1, True, False), (132, 9, False, True),
+                                                  (200, 4, False, False), (36, 2, True, True)])
+def test_stream_kernel_ragged_shapes(lsi_mods, W, L, packed, with_mask):
+    """Streaming splat kernel on ragged rows (W not a multiple of the 64-pixel segment / of 4), more than one layer
+    group (L > 4), both layouts and masks, general and rectified poses: must match the plain atomic kernel."""
+    ldi, helpers = lsi_mods['ldi'], lsi_mods['helpers']
+    B, H = 3, 17
+    gen = torch.Generator().manual_seed(W * 131 + L)
+    tex = torch.rand(L, B, H, W, 3, generator=gen).cuda()
+    disp = (torch.rand(L, B, H, W, 1, generator=gen) * 0.9 + 0.05).cuda()
+    mask = (torch.rand(L, B, H, W, 1, generator=gen) > 0.3).float().cuda() if with_mask else torch.ones(L, B, H, W, 1).cuda()
+    if not with_mask:
+        mask._lsi_all_ones = True
+    if packed:
+        pk = torch.cat([tex, disp], dim=-1)
+        tex, disp = pk[..., :3], pk[..., 3:]
+    k = torch.tensor([[W * 0.8, 0, W / 2], [0, W * 0.8, H / 2], [0, 0, 1]], dtype=torch.float32).repeat(B, 1, 1).cuda()
+    rot = torch.eye(3).repeat(B, 1, 1)
+    ang = 0.03
+    rot[1] = torch.tensor([[1, 0, 0], [0, math.cos(ang), -math.sin(ang)], [0, math.sin(ang), math.cos(ang)]])
+    rot[2] = torch.tensor([[math.cos(ang), 0, math.sin(ang)], [0, 1, 0], [-math.sin(ang), 0, math.cos(ang)]])
+    t = torch.tensor([[0.3, 0, 0], [0.1, -0.05, 0.02], [-0.2, 0.1, 0.05]]).reshape(B, 3, 1)
+    pc = helpers.pixel_coords(B, H, W)
+    for compose in (True, False):
+        kw = dict(compose_layers=compose, trg_downsampling=1, bg_layer_disp=0.01, max_disp=1.0, zbuf_scale=10.0)
+        a = ldi.forward_splat((tex, mask, disp), pc, k, k, rot.cuda(), t.cuda(), **kw)
+        b = ldi.forward_splat((tex, mask, disp), pc, k, k, rot.cuda(), t.cuda(), _variant=1, **kw)
+        for x, y in zip(a, b):
+            assert torch.isfinite(x).all()
+            assert rel_err(x.cpu(), y.cpu()) < 1e-5

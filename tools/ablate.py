@@ -1,5 +1,6 @@
 """Ablation timings of the forward splat kernel (measurement aid): variant 0 = real kernel, 1 = plain atomic kernel,
-101 = no reductions, 102 = loads + one coalesced reduction per pixel."""
+3 = ring-less reduction kernel, 101 = no reductions, 102 = loads + one coalesced reduction per pixel (both on the
+ring-less kernel).  ABLATE_PACKED=1 uses the packed head-output layout."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'layered-scene-inference_b200')); sys.path.insert(0, ROOT)
@@ -15,7 +16,10 @@ masks = torch.ones(bench.L, B, bench.H, bench.W, 1, device='cuda'); masks._lsi_a
 cam = [torch.tensor(host[k], device='cuda') for k in ('k_s', 'k_t', 'rot', 't')]
 pc = helpers.pixel_coords(B, bench.H, bench.W)
 lib = _b200.lib()
-variants = [int(v) for v in sys.argv[1:]] or [0, 1, 101, 102]
+variants = [int(v) for v in sys.argv[1:]] or [0, 3, 1, 101, 102]
+if os.environ.get('ABLATE_PACKED'):   # the head-output layout [L,B,H,W,4] = (r,g,b,disp)
+    pk = torch.cat([tex, disp], dim=-1)
+    tex, disp = pk[..., :3], pk[..., 3:]
 for ds in (1.0, 0.5):
     for v in variants:
         def step():

@@ -19,11 +19,15 @@ ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--backward', action='store_true')
 ap.add_argument('--ds', type=float, default=1.0)
 ap.add_argument('--variant', type=int, default=0)
+ap.add_argument('--packed', action='store_true')
 a = ap.parse_args()
 B = a.batch
 host = bench.make_inputs(B, 0)
 tex = torch.tensor(host['tex'], device='cuda').requires_grad_(a.backward)
 disp = torch.tensor(host['disp'], device='cuda').requires_grad_(a.backward)
+if a.packed:
+    pk = torch.cat([tex, disp], dim=-1)
+    tex, disp = pk[..., :3], pk[..., 3:]
 masks = torch.ones(bench.L, B, bench.H, bench.W, 1, device='cuda')
 masks._lsi_all_ones = True
 cam = [torch.tensor(host[k], device='cuda') for k in ('k_s', 'k_t', 'rot', 't')]

@@ -25,9 +25,18 @@ pc = helpers.pixel_coords(B, bench.H, bench.W)
 d = ldi_pred[2]
 print('disp stats: mean %.4f std %.4f; mean |dx| %.5f (in target px: %.3f)' % (float(d.mean()), float(d.std()), float((d[:, :, :, 1:] - d[:, :, :, :-1]).abs().mean()),
       float((d[:, :, :, 1:] - d[:, :, :, :-1]).abs().mean()) * 257.0))
+import ctypes
+from lsi import _b200
+lib = _b200.lib()
+lib.lsi_b200_kernel_timing_enable(1)
 for _ in range(a.iters):
     with torch.no_grad():
         ldi.forward_splat(tuple(ldi_pred), pc, *cam, compose_layers=True, trg_downsampling=1.0, bg_layer_disp=bench.BG_DISP,
                           max_disp=bench.MAX_DISP, zbuf_scale=bench.ZBUF_SCALE)
 torch.cuda.synchronize()
+kms, kn = (ctypes.c_double * 8)(), (ctypes.c_int * 8)()
+_b200.call('lsi_b200_kernel_timing_collect', ctypes.cast(kms, ctypes.c_void_p), ctypes.cast(kn, ctypes.c_void_p))
+lib.lsi_b200_kernel_timing_enable(0)
+gb = 4.0 * 4 * bench.L * bench.H * bench.W * B / 1e9
+print('noisy LDI, B=%d: splat %.4f ms/call (%.0f GB/s), normalize %.4f ms/call' % (B, kms[0] / a.iters, gb / (kms[0] / a.iters * 1e-3), kms[1] / a.iters))
 print('done')
