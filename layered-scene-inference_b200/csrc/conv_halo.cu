@@ -43,6 +43,9 @@ struct HaloParams {
   int chunks, kh, kw, stride, pad_t, pad_l, mode;
   int n_tile, epilogue, stages;
   int f16;                   // 1: transform warps also convert the normalised tile to fp16 in place; MMAs run kind::f16
+  int in_f16;                // 1: the input tensor is stored as fp16 (RAW output of a producer run with out_f16): 64-byte rows,
+                             //    64B swizzle, normalised in place by the transform warps (implies f16)
+  int out_f16;               // 1: the RAW output is stored as fp16 (its only consumer normalises on load and feeds fp16 MMAs anyway)
   int halo_w, halo_h;
   uint32_t halo_bytes, b_tap_bytes, w_bytes, div_halo_w;
 };
@@ -201,6 +204,55 @@ __device__ __forceinline__ void transform_tile(float4* tile, const float* bn_a, 
   }
 }
 
+// fp16 input tile: halo_w * halo_h pixel rows of 64 bytes (32 fp16 channels), 64B-swizzled as TMA wrote it: 16-byte chunk c
+// of row p sits at chunk position c ^ ((p >> 1) & 3).  thread -> (chunk position j, pixels p0, p0 + kNT/4, ...): the pixel
+// step is a multiple of 8, so the logical chunk -- hence the eight channels this thread touches -- is fixed and their
+// scale/shift live in registers.  Normalised in place (no layout change: the MMA reads the same SWIZZLE_64B K-major tile).
+template <bool kInterior, int kNT>
+__device__ __forceinline__ void transform_tile_h(uint4* tile, const float* bn_a, const float* bn_b, int tid, const HaloParams& p,
+                                                 int ys0, int xs0) {
+  const int j = tid & 3, p0 = tid >> 2;
+  const int jl = j ^ ((p0 >> 1) & 3);                        // logical chunk = channels 8*jl .. 8*jl+7
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; k += 4) {
+    const float4 a4 = *reinterpret_cast<const float4*>(bn_a + (jl << 3) + k);
+    const float4 b4 = *reinterpret_cast<const float4*>(bn_b + (jl << 3) + k);
+    a[k] = a4.x; a[k + 1] = a4.y; a[k + 2] = a4.z; a[k + 3] = a4.w;
+    b[k] = b4.x; b[k + 1] = b4.y; b[k + 2] = b4.z; b[k + 3] = b4.w;
+  }
+  const int npx = p.halo_w * p.halo_h;
+  constexpr int kRows = kNT / 4;                             // pixel rows covered per pass
+  uint4* q = tile + tid;                                     // item k lives at q + kNT * k
+  for (int k0 = 0; p0 + kRows * k0 < npx; k0 += 2) {
+    uint4 v[2]; bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ok[u] = p0 + kRows * (k0 + u) < npx;
+      v[u] = ok[u] ? q[kNT * (k0 + u)] : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      bool inb = ok[u];
+      if (!kInterior) {
+        const int pxl = p0 + kRows * (k0 + u);
+        const int hy = (int)(((uint32_t)pxl * p.div_halo_w) >> 16), hx = pxl - hy * p.halo_w;
+        inb = inb && (unsigned)(ys0 + hy) < (unsigned)p.Hin && (unsigned)(xs0 + hx) < (unsigned)p.Win;
+      }
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        const float y0 = inb ? fmaxf(fmaf(f.x, a[2 * k], b[2 * k]), 0.f) : 0.f;
+        const float y1 = inb ? fmaxf(fmaf(f.y, a[2 * k + 1], b[2 * k + 1]), 0.f) : 0.f;
+        o[k] = pack_half2(y0, y1);
+      }
+      if (ok[u]) q[kNT * (k0 + u)] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // kWide: n_tile == 64 (two 32-column passes per accumulator, two sets of statistics registers)
 template <bool kWide>
 __global__ void __launch_bounds__(kWide ? kThreadsWide : kThreads, kWide ? 1 : 2)
@@ -274,7 +326,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
                         ((ky0 + i * s) * p.kw + (kx0 + j * s)) * p.n_tile);
       Ring r(p.stages);
-      const uint32_t tx = (uint32_t)(p.halo_w * p.halo_h) * 128u;
+      const uint32_t tx = (uint32_t)(p.halo_w * p.halo_h) * (p.in_f16 ? 64u : 128u);
       TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
       for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ti.next()) {
         const int n_img = ti.n, y0 = ti.ty * kTH, x0 = ti.tx * kTW;
@@ -292,7 +344,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // (kind::f16: A/B format F16 = 0, two K = 16 steps per 32-channel chunk)
       const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
                                    : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
-      const uint64_t hi_a = umma_desc_hi((uint32_t)p.halo_w * 128u), hi_b = p.f16 ? umma_desc_hi_sw64() : umma_desc_hi(1024u);
+      // fp16-stored input: 64-byte rows with the 64B swizzle, 8-row groups halo_w rows apart; same shifted-start trick
+      const uint32_t row_b = p.in_f16 ? 64u : 128u;
+      const uint64_t hi_a = p.in_f16 ? (((uint64_t)1 << 16) | ((uint64_t)(((uint32_t)p.halo_w * 64u) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61))
+                                     : umma_desc_hi((uint32_t)p.halo_w * 128u);
+      const uint64_t hi_b = p.f16 ? umma_desc_hi_sw64() : umma_desc_hi(1024u);
       mbar_wait(wfull, 0);
       const uint64_t b_desc0 = umma_desc(hi_b, smem_u32(s_w));
       Ring r(p.stages);
@@ -312,7 +368,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int dy = (p.mode == 0) ? i : nky - 1 - i;
             for (int j = 0; j < nkx; ++j) {
               const int dx = (p.mode == 0) ? j : nkx - 1 - j;
-              const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * 128u) >> 4);
+              const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * row_b) >> 4);
               const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes) >> 4);
               if (p.f16) {
 #pragma unroll
@@ -424,7 +480,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
           if (oy < p.Hp && ox < p.Wp) {
             if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
-            *reinterpret_cast<float4*>(p.out + ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4) = v;
+            const size_t e = ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4;
+            if (p.out_f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + e) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+            else *reinterpret_cast<float4*>(p.out + e) = v;
           }
         }
         if (cc == 0) {
@@ -467,7 +525,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float4* tile = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes);
         const float* ta = bn_a + ch * kKC; const float* tb = bn_b + ch * kKC;
         constexpr int kNT = kWide ? 256 : 128;
-        if (p.f16) {
+        if (p.in_f16) {
+          if (interior) transform_tile_h<true, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
+          else transform_tile_h<false, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
+        } else if (p.f16) {
           if (interior) transform_tile<true, true, kNT>(tile, ta, tb, tid, p, ys0, xs0);
           else transform_tile<true, false, kNT>(tile, ta, tb, tid, p, ys0, xs0);
         } else {
@@ -558,7 +619,7 @@ struct HaloPlan {
   size_t smem;
 };
 
-bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false) {
+bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool in_f16 = false) {
   if (!d) return false;
   if (d->c_in % kKC != 0 || d->c_in > kMaxCin || d->c_in < kKC) return false;
   if (d->mode != 0 && d->mode != 1) return false;
@@ -574,7 +635,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false) {
   pl->nky_max = (d->kh + s - 1) / s; pl->nkx_max = (d->kw + s - 1) / s;
   if (pl->nky_max * pl->nkx_max > 9) return false;
   pl->halo_w = kTW + pl->nkx_max - 1; pl->halo_h = kTH + pl->nky_max - 1;
-  pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * 128u + 1023u) & ~1023u;
+  pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * (in_f16 ? 64u : 128u) + 1023u) & ~1023u;
   pl->b_tap_bytes = ((uint32_t)pl->n_tile * (f16 ? 64u : 128u) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows
   pl->w_bytes = (uint32_t)(pl->nky_max * pl->nkx_max * pl->chunks) * pl->b_tap_bytes;
   const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + 4 * 32 * kStgPitch * sizeof(float);
@@ -616,20 +677,22 @@ extern "C" size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc*
   return (size_t)d->kh * d->kw * pl.n_tile * (size_t)d->c_in * sizeof(float) + 512 + halo_stat_part_bytes(pl.n_tile);
 }
 
-extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats, const float* in_bn_beta,
-                                    const float* w, const float* bias, const float* out_scale, float* out, float* out_bn_stats,
-                                    float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
+static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_f16, const float* in_bn_stats, const float* in_bn_beta,
+                           const float* w, const float* bias, const float* out_scale, void* out, int out_f16, float* out_bn_stats,
+                           float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
   LSI_REQUIRE(d && in && w && out && workspace, "NULL pointer argument");
   HaloPlan pl;
   LSI_REQUIRE(halo_plan(d, &pl), "shape not supported by the halo-tile tensor-core path");
+  LSI_REQUIRE(!in_f16 || (in_bn_stats && d->in_c_stride % 8 == 0), "fp16-stored input needs the producer's batch-norm statistics and an 8-channel-aligned pixel stride");
+  LSI_REQUIRE(!out_f16 || (pl.n_tile == d->c_out && d->epilogue == 0), "fp16-stored output is for plain 32/64-channel conv outputs");
   LSI_REQUIRE((in_bn_stats == nullptr) == (in_bn_beta == nullptr), "in_bn_stats and in_bn_beta go together");
   // fp16 operands (same 10-bit mantissa as TF32, fp32 accumulation) whenever the transform warps rewrite the tile anyway:
   // normalised post-ReLU activations are O(1), far inside fp16's range; halves the operand bytes the MMAs pull from
   // shared memory, the resource these layers are bound by
   static int f16_on = -1;
   if (f16_on < 0) { const char* e = getenv("LSI_B200_HALO_F16"); f16_on = (e && atoi(e) == 0) ? 0 : 1; }
-  const bool f16 = in_bn_stats != nullptr && f16_on == 1;
-  if (f16) { LSI_REQUIRE(halo_plan(d, &pl, true), "halo plan (fp16) failed"); }
+  const bool f16 = in_bn_stats != nullptr && (f16_on == 1 || in_f16);
+  if (f16) { LSI_REQUIRE(halo_plan(d, &pl, true, in_f16 != 0), "halo plan (fp16) failed"); }
   LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
   LSI_REQUIRE(!out_bn_stats || (d->epilogue == 0 && pl.n_tile == d->c_out), "bn statistics need a plain 32/64-channel conv output");
   LSI_REQUIRE(workspace_bytes >= lsi_b200_conv2d_halo_workspace_bytes(d), "workspace too small");
@@ -642,14 +705,14 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   const int s = d->mode == 1 ? d->stride : 1;
   HaloParams p;
   LSI_REQUIRE(!out_scale || pl.n_tile == 16, "out_scale is supported on the <= 4-channel output path only");
-  p.out = out; p.bias = bias; p.out_scale = out_scale; p.in_stats = in_bn_stats; p.in_beta = in_bn_beta; p.stat_part = nullptr;
+  p.out = static_cast<float*>(out); p.bias = bias; p.out_scale = out_scale; p.in_stats = in_bn_stats; p.in_beta = in_bn_beta; p.stat_part = nullptr;
   p.Hin = d->h_in; p.Win = d->w_in; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
   p.Hp = d->h_out / s; p.Wp = d->w_out / s;
   p.tiles_x = (p.Wp + kTW - 1) / kTW;
   const int tiles_y = (p.Hp + kTH - 1) / kTH;
   p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
   p.chunks = pl.chunks; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
-  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0;
+  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0; p.in_f16 = in_f16 ? 1 : 0; p.out_f16 = out_f16 ? 1 : 0;
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
   p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
 
@@ -670,13 +733,14 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
   CUtensorMap map_a, map_w;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->c_in, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_c_stride * 4, (cuuint64_t)d->w_in * d->in_c_stride * 4,
-                             (cuuint64_t)d->h_in * d->w_in * d->in_c_stride * 4};
+    const cuuint64_t eb = in_f16 ? 2 : 4;
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_c_stride * eb, (cuuint64_t)d->w_in * d->in_c_stride * eb,
+                             (cuuint64_t)d->h_in * d->w_in * d->in_c_stride * eb};
     cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)pl.halo_w, (cuuint32_t)pl.halo_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(&map_a, in_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(in), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, in_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
   {
@@ -717,4 +781,19 @@ extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in
     LSI_LAUNCH_CHECK();
   }
   return LSI_B200_OK;
+}
+
+extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats, const float* in_bn_beta,
+                                    const float* w, const float* bias, const float* out_scale, float* out, float* out_bn_stats,
+                                    float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
+  return conv2d_halo_impl(d, in, 0, in_bn_stats, in_bn_beta, w, bias, out_scale, out, 0, out_bn_stats, bn_eps, workspace,
+                          workspace_bytes, stream);
+}
+
+extern "C" int lsi_b200_conv2d_halo_h(const lsi_b200_conv_desc* d, const void* in, int in_f16, const float* in_bn_stats,
+                                      const float* in_bn_beta, const float* w, const float* bias, const float* out_scale, void* out,
+                                      int out_f16, float* out_bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  return conv2d_halo_impl(d, in, in_f16, in_bn_stats, in_bn_beta, w, bias, out_scale, out, out_f16, out_bn_stats, bn_eps, workspace,
+                          workspace_bytes, stream);
 }

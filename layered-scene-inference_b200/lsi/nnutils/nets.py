@@ -214,6 +214,7 @@ def _wgrad(desc_kw, big, small, dw):
 
 
 _HALO = os.environ.get('LSI_B200_CONV_HALO', '1') != '0'
+_HALO_F16_STORE = os.environ.get('LSI_B200_HALO_F16_STORE', '1') != '0'
 _OUT_SCALE_CACHE = {}
 
 
@@ -238,6 +239,8 @@ class _Pending(object):
 
     def materialize(self):
         z = self.z
+        if z.dtype != torch.float32:     # fp16-stored raw output met a consumer that cannot normalise on load
+            z = z.float()
         B, H, W, C = z.shape
         _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(self.beta), _b200.ptr(z), _b200.ptr(self.stats),
                    B * H * W, C, C, C, BN_EPS, 1, 1, _b200.ptr(_bn_workspace(z.device, C)), _b200.stream())
@@ -261,9 +264,10 @@ def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None):
     xin = x.z if pend else x
     nws = int(lib.lsi_b200_conv2d_halo_workspace_bytes(d))
     ws = _tc_workspace(xin.device, nws)
-    _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(xin), _b200.ptr(x.stats) if pend else None,
-               _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out_scale), _b200.ptr(out),
-               _b200.ptr(out_stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+    _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), int(xin.dtype == torch.float16),
+               _b200.ptr(x.stats) if pend else None, _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias),
+               _b200.ptr(out_scale), _b200.ptr(out), int(out.dtype == torch.float16), _b200.ptr(out_stats), BN_EPS,
+               _b200.ptr(ws), ws.numel(), _b200.stream())
 
 
 class _Geometry(object):
@@ -427,7 +431,10 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
         dev = a.device
         done = False
         if not pair and _halo_ok(d, a.z if isinstance(a, _Pending) else a):
-            z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float32, device=dev)
+            # the raw output of a 32-channel head layer is read by exactly one consumer, a halo-kernel conv that
+            # normalises it on load and feeds fp16 MMAs: store it as fp16 (half the bytes of these byte-bound layers)
+            z_dt = torch.float16 if (defer and _HALO_F16_STORE and cout == 32) else torch.float32
+            z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=z_dt, device=dev)
             stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
             _conv_halo(d, a, w, z, out_stats=stats)
             done = True

@@ -12,7 +12,7 @@ TOL = 2e-3
 EPS = 1e-3
 
 
-def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=None, seed=0):
+def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=None, seed=0, in_f16=False, out_f16=False):
     from lsi import _b200
     from lsi.nnutils.nets import same_pad
     lib = _b200.lib()
@@ -34,6 +34,8 @@ def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=Non
               pad_left=pl, mode=mode, in_c_stride=Cin, out_c_stride=Cout, epilogue=epilogue, accumulate=0, **ws)
     d = _b200.ConvDesc(**kw)
     assert lib.lsi_b200_conv2d_halo_supported(d) == 1
+    if in_f16:                 # the producer stored its raw output as fp16: the reference sees the same rounded values
+        x = x.half().float()
     if bn_in:
         mean = x.mean(dim=(0, 1, 2)); var = x.var(dim=(0, 1, 2), unbiased=False)
         in_stats = torch.stack([mean, torch.rsqrt(var + EPS)], dim=1).contiguous()
@@ -44,14 +46,19 @@ def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=Non
         xn = x
     ref = torch.zeros(B, Ho, Wo, Cout, device=dev)
     _b200.call('lsi_b200_conv2d', d, _b200.ptr(xn), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(ref), _b200.stream())
-    out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev)
+    out = torch.full((B, Ho, Wo, Cout), 7.0, device=dev, dtype=torch.float16 if out_f16 else torch.float32)
     st = torch.zeros(Cout, 2, device=dev) if stats_out else None
     nws = lib.lsi_b200_conv2d_halo_workspace_bytes(d)
     wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
-    _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w), _b200.ptr(bias),
-               None, _b200.ptr(out), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
+    if in_f16 or out_f16:
+        xin = x.half() if in_f16 else x
+        _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), int(in_f16), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w),
+                   _b200.ptr(bias), None, _b200.ptr(out), int(out_f16), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
+    else:
+        _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w), _b200.ptr(bias),
+                   None, _b200.ptr(out), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
     torch.cuda.synchronize()
-    return out, ref, st
+    return out.float(), ref, st
 
 
 def _check(out, ref, st):
@@ -94,6 +101,30 @@ def test_upconv_4x4_s2(B, H, W, Cin, Cout, bn_in):
 ])
 def test_prediction_conv_bias_sigmoid(B, H, W, out_hw, bn_in):
     out, ref, _ = _run(B, H, W, 32, 4, 3, 0, bn_in, False, epilogue=2, out_hw=out_hw)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k,mode,in_f16,out_f16', [
+    (1, 16, 8, 32, 32, 3, 0, True, True),       # upcnv1b between two fp16-stored tensors, one tile
+    (2, 21, 37, 32, 32, 3, 0, True, True),      # ragged
+    (4, 128, 160, 32, 32, 3, 0, True, False),   # ring wraps
+    (2, 16, 24, 64, 32, 4, 1, False, True),     # upcnv1 writes fp16
+    (1, 19, 11, 64, 32, 4, 1, True, True),      # up-conv reading fp16 (two chunks per tile)
+    (2, 32, 24, 128, 64, 4, 1, True, False),    # four chunks, wide variant
+])
+def test_fp16_stored_activations(B, H, W, Cin, Cout, k, mode, in_f16, out_f16):
+    """RAW activations stored as fp16 between halo layers (lsi_b200_conv2d_halo_h): same result as the fp32-stored path up to
+    the fp16 rounding of the stored values (2^-11 relative)."""
+    out, ref, st = _run(B, H, W, Cin, Cout, k, mode, True, True, in_f16=in_f16, out_f16=out_f16)
+    assert rel_err(out.cpu(), ref.cpu()) < (3e-3 if out_f16 else TOL)
+    _check(ref, ref, None)
+    mean = ref.mean(dim=(0, 1, 2)); var = ref.var(dim=(0, 1, 2), unbiased=False)
+    assert rel_err(st[:, 0].cpu(), mean.cpu()) < TOL
+    assert rel_err(st[:, 1].cpu(), torch.rsqrt(var + EPS).cpu()) < TOL
+
+
+def test_fp16_stored_prediction_input():
+    out, ref, _ = _run(2, 32, 48, 32, 4, 3, 0, True, False, epilogue=2, out_hw=(32, 40), in_f16=True)
     assert rel_err(out.cpu(), ref.cpu()) < TOL
 
 
