@@ -33,7 +33,7 @@ H, W, L, B_PER_GPU = 256, 832, 4, 64
 MAX_DISP, BG_DISP, ZBUF_SCALE, DS = 0.4, 1e-3, 50.0, 1.0      # kitti constants, ldi_enc_dec.py:421-425
 METRIC = 'rendered views/sec at 256x832x4-layer'
 WORKLOAD = ('KITTI-like 256x832 image -> encoder-decoder U-Net + 4 LDI heads (W zero-padded to 896 for the U-Net, '
-            'prediction cropped; TF32 tcgen05 convs, batch-stat BN) -> forward_splat(compose_layers=True, '
+            'prediction cropped; tcgen05 convs with fp16 operands/activations and fp32 accumulation, batch-stat BN) -> forward_splat(compose_layers=True, '
             'trg_downsampling=1) -> rendered target view; batch %d per GPU' % B_PER_GPU)
 
 
@@ -209,6 +209,10 @@ def main():
     pc = helpers.pixel_coords(B, H, W, device=dev)
     opts = train_utils.default_opts(dataset='kitti', n_layers=L, batch_size=B, img_height=H, img_width=W,
                                     zbuf_scale=ZBUF_SCALE)
+    # inference-only conv mode: fp16 activations in HBM + kind::f16 tcgen05 MMAs, fp32 accumulation and statistics (same
+    # mantissa as a TF32 operand; the bench contract asks for >= bf16).  With autograd enabled (the training step measured
+    # below) the mode is TF32.  BENCH_CONV_MODE=tf32 reproduces the all-fp32-activation numbers.
+    nets.set_conv_mode(os.environ.get('BENCH_CONV_MODE', 'f16'))
     store = nets.ParamStore(device=dev, seed=0)           # random-init weights of the reference architecture
     kw = dict(compose_layers=True, trg_downsampling=DS, bg_layer_disp=BG_DISP, max_disp=MAX_DISP, zbuf_scale=ZBUF_SCALE)
     with torch.no_grad():
@@ -259,17 +263,17 @@ def main():
     splat_bytes_per_step = 4.0 * 4 * L * n_src * B          # packed (r,g,b,disp) head output read once by the splat kernel
     splat_ms = kms[0] / args.steps
     achieved = splat_bytes_per_step / (splat_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'splat_fwd_fast_kernel (forward splat; %d launches per step)' % (kn[0] // args.steps),
+    roofline = {'bound': 'hbm', 'kernel': 'splat_fwd_stream_kernel (forward splat; %d launches per step)' % (kn[0] // args.steps),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'traffic': None, 'algorithmic_bytes_per_step': splat_bytes_per_step, 'kernel_ms_per_step': splat_ms,
                 'normalize_ms_per_step': kms[1] / args.steps}
     wp = -(-W // 128) * 128
     conv_flops = (21.8e9 + 23.0e9 * L) * (H * wp) / (256.0 * 768.0) * B      # forward 2*MAC per step
     conv_ms = (kms[4] + kms[5]) / args.steps
-    conv = {'bound': 'tensor', 'kernel': 'conv_tc_kernel + conv_halo_kernel (tcgen05 TF32, TMA) + fp32 stem', 'achieved': conv_flops / (conv_ms * 1e-3) / 1e12,
+    conv = {'bound': 'tensor', 'kernel': 'conv_tc_kernel + conv_halo_kernel (tcgen05 kind::%s, TMA) + fp32 stem' % ('f16' if nets.get_conv_mode() == 'f16' else 'tf32'), 'achieved': conv_flops / (conv_ms * 1e-3) / 1e12,
             'unit': 'TFLOP/s', 'kernel_ms_per_step': conv_ms, 'tc_ms_per_step': kms[4] / args.steps,
             'fp32_ms_per_step': kms[5] / args.steps, 'flops_per_step': conv_flops,
-            'share_of_step': conv_ms / ms_per_step, 'note': 'TF32 dense peak is ~half of the measured bf16 peak in MEASURED_PEAKS.json'}
+            'share_of_step': conv_ms / ms_per_step, 'note': 'dense fp16 peak = the measured bf16 figure in MEASURED_PEAKS.json (1653 TFLOP/s burst); TF32 about half of it'}
 
     # --- renderer slice alone (the kernel the roofline is about), LDIs resident in HBM ------------------------------
     with torch.no_grad():
@@ -380,7 +384,7 @@ def main():
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'views/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'tf32 convs (fp32 accumulate) + f32 renderer', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': ('f16 conv operands/activations (fp32 accumulate, fp32 batch statistics)' if nets.get_conv_mode() == 'f16' else 'tf32 convs (fp32 accumulate)') + ' + f32 renderer', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'h': H, 'w': W, 'layers': L, 'batch_per_gpu': B, 'global_batch': world * B,
                        'parallelism': 'dp%d (independent views per rank, no data-path collective at inference)' % world,
                        'l2_policy': 'per-step activations (several GB) exceed the 126 MB L2'},

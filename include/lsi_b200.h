@@ -210,6 +210,19 @@ LSI_B200_API int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const f
                                             int in_b_c_stride, const float* w, float* out, float* bn_stats, float bn_eps,
                                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Inference-only fp16 mode (lsi.nnutils.nets.set_conv_mode('f16')): lsi_b200_conv2d_tc / _bnstats with fp16 activations
+ * (in_a, in_b and -- when out_f16 != 0 -- out are __half tensors; strides in elements, multiples of 8), weights rounded to
+ * fp16 on the fly, kind::f16 tcgen05 MMAs with fp32 accumulation; bn_stats (optional) as in lsi_b200_conv2d_tc_bnstats, reduced
+ * from the fp32 accumulators.  bias may be NULL when epilogue == 0. */
+LSI_B200_API int lsi_b200_conv2d_tc_h(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b,
+                                      int in_b_c_stride, const float* w, const float* bias, void* out, int out_f16,
+                                      float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* y (__half, dense [n_pixels, channels]) = relu((x - mean) * rstd + beta) with given stats[c] = (mean, rstd); x is __half
+ * (x_f16 != 0) or float; channels % 8 == 0.  The normalise pass of the fp16 mode (slim.batch_norm + ReLU, nets.py:263-272). */
+LSI_B200_API int lsi_b200_bn_relu_apply_h(const void* x, int x_f16, const float* beta, const float* stats, void* y,
+                                          long long n_pixels, int channels, void* stream);
+
 /* Halo-tile tensor-core convolution for the full-resolution few-channel layers of the LDI heads (nets.py:87-114: upcnv1
  * 4x4/2 up-conv 64->32, upcnv1b 3x3 32->32; nets.py:137-159: pred 3x3 32->4 + bias + sigmoid): unit-stride gathers
  * (mode 0 stride 1, or mode 1), c_in in {32,64,96,128}, c_out in {32,64} or <= 4 with out_c_stride 4.  The filter bank

@@ -15,6 +15,7 @@
 //               warps 2-5 = epilogue (tcgen05.ld -> bias/sigmoid/accumulate -> 128-bit global stores).
 //   accumulate  TMEM, 128 lanes x N fp32 columns.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "capi_common.h"
 #include "common.cuh"
@@ -40,6 +41,8 @@ struct TcParams {
   int halo_w;                 // xm: pixels per halo row (tile width 8 + taps along x - 1, or padded to 16)
   int th, tw;                 // tile height / width in pixels (8x16 default, 16x8 with xm)
   float* stat_part;           // [gridDim.x*4][n_pad][2] per-(CTA,warp) channel sums of the output (batch-norm statistics), or NULL
+  int h16;                    // 1: fp16 activations and weights (64-byte rows, 64B swizzle, kind::f16 MMAs, K = 16)
+  int out_f16;                // 1: plain outputs are stored as fp16
   int stages;                 // smem ring depth (2..4): shallower rings let 2-3 CTAs share an SM so that one CTA's
                               // prologue/epilogue overlaps another's main loop
 };
@@ -95,6 +98,30 @@ __device__ __forceinline__ uint64_t umma_desc_shifted(uint32_t saddr, uint32_t s
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+// generic form: layout 2 = SWIZZLE_128B (128-byte rows), 4 = SWIZZLE_64B (64-byte rows: 32 fp16 channels); the shifted-start
+// property above holds for both (tests/test_gpu_conv_tc.py, test_gpu_conv_halo.py)
+__device__ __forceinline__ uint64_t umma_desc_any(uint32_t saddr, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -158,9 +185,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_tap_bytes = ((uint32_t)p.n_tile * 128 + 1023) & ~1023u;
-  const uint32_t a_bytes = p.xm ? (uint32_t)p.halo_w * p.th * 128 : kTileM * 128;
-  const uint32_t b_bytes = (uint32_t)p.n_tile * 128;
+  const uint32_t rb = p.h16 ? 64u : 128u;        // bytes of one 32-channel operand row
+  const uint32_t b_tap_bytes = ((uint32_t)p.n_tile * rb + 1023) & ~1023u;
+  const uint32_t a_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb : kTileM * rb;
+  const uint32_t b_bytes = (uint32_t)p.n_tile * rb;
   const uint32_t stage_bytes = p.xm ? a_bytes + (uint32_t)p.kw * b_tap_bytes : a_bytes + b_tap_bytes;   // xm: up to kw weight tiles
   const int kStages = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
@@ -239,7 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (elect_one()) {
       // ---------------- MMA issuer ----------------
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      // (kind::f16: A/B format F16 = 0, two K = 16 steps per 32-channel chunk)
+      const uint32_t idesc = p.h16 ? ((1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
+                                   : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
+      const uint32_t layout = p.h16 ? 4u : 2u, sbo_dense = p.h16 ? 512u : 1024u;
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const TileCoord c = tile_coord(p, tile, s);
@@ -257,19 +288,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // 256 KB, so there is no carry out of its 14 bits
           const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + a_bytes;
           if (p.xm) {
-            const uint64_t ad0 = umma_desc_shifted(sa, (uint32_t)p.halo_w * 128), bd0 = umma_desc(sb);
+            const uint64_t ad0 = umma_desc_any(sa, (uint32_t)p.halo_w * rb, layout), bd0 = umma_desc_any(sb, sbo_dense, layout);
             for (int j = 0; j < c.nkx; ++j) {
               const uint32_t off = (p.mode == 0) ? (uint32_t)j : (uint32_t)(c.nkx - 1 - j);   // pixels into the halo row
-              const uint64_t ad = ad0 + (uint64_t)(off * 8u), bd = bd0 + (uint64_t)(((uint32_t)j * b_tap_bytes) >> 4);
+              const uint64_t ad = ad0 + (uint64_t)(off * (rb >> 4)), bd = bd0 + (uint64_t)(((uint32_t)j * b_tap_bytes) >> 4);
+              if (p.h16) {
 #pragma unroll
-              for (int kk = 0; kk < kKC / 8; ++kk)
-                umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
+                for (int kk = 0; kk < kKC / 16; ++kk)
+                  umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < kKC / 8; ++kk)
+                  umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
+              }
             }
           } else {
-            const uint64_t ad = umma_desc(sa), bd = umma_desc(sb);
+            const uint64_t ad = umma_desc_any(sa, sbo_dense, layout), bd = umma_desc_any(sb, sbo_dense, layout);
+            if (p.h16) {
 #pragma unroll
-            for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
-              umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+              for (int kk = 0; kk < kKC / 16; ++kk)     // UMMA K = 16 for fp16: 32 bytes along the swizzled row
+                umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < kKC / 8; ++kk)      // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+                umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
             }
           }
           umma_commit(&empty[st]);                 // frees the stage once these MMAs have read it
@@ -340,7 +382,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int rr = 0; rr < 32; ++rr) { const float v = stg[rr * 33 + lane]; a += v; b2 = fmaf(v, v, b2); }
           ssum[cc >> 5] += a; ssq[cc >> 5] += b2;
         }
-        if (in_range) {
+        if (in_range && p.out_f16) {   // plain conv output (host guarantees epilogue 0, no accumulate, Co % 8 == 0), stored as fp16
+          const int nvalid = min(min(32, p.n_tile - cc), p.Co - (c.n0 + cc));
+          __half* dh = reinterpret_cast<__half*>(p.out) + ((size_t)(c.n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0 + cc;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (j < nvalid)
+              *reinterpret_cast<uint4*>(dh + j) = make_uint4(pack_half2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                                             pack_half2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
+                                                             pack_half2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5])),
+                                                             pack_half2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7])));
+        } else if (in_range) {
           const int nvalid = min(min(32, p.n_tile - cc), p.Co - (c.n0 + cc));
           if (nvalid == 32 && p.epilogue == 0 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst + cc) & 15) == 0)) {
 #pragma unroll
@@ -380,6 +432,18 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
     const int co = (int)((i / cin) % n_pad);
     const int tap = (int)(i / ((long long)cin * n_pad));
     wk[i] = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+  }
+}
+
+// same, rounded to fp16 (operand type of the kind::f16 path)
+__global__ void __launch_bounds__(256) prep_weights_f16_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
+                                                               int cout, int n_pad, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * n_pad * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % n_pad);
+    const int tap = (int)(i / ((long long)cin * n_pad));
+    wk[i] = __float2half_rn((co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f);
   }
 }
 
@@ -463,9 +527,9 @@ __global__ void __launch_bounds__(256) finalize_stats_f32_kernel(const float* __
 }
 }  // namespace lsi
 
-static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b, int in_b_c_stride,
-                          const float* w, const float* bias, float* out, float* bn_stats, float bn_eps, void* workspace,
-                          size_t workspace_bytes, void* stream);
+static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
+                          const float* w, const float* bias, void* out, float* bn_stats, float bn_eps, void* workspace,
+                          size_t workspace_bytes, void* stream, int h16 = 0, int out_f16 = 0);
 
 extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
                                   int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
@@ -482,10 +546,13 @@ extern "C" int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const flo
   return conv2d_tc_impl(d, in_a, c_in_a, in_b, in_b_c_stride, w, nullptr, out, bn_stats, bn_eps, workspace, workspace_bytes, stream);
 }
 
-static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b, int in_b_c_stride,
-                          const float* w, const float* bias, float* out, float* bn_stats, float bn_eps, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
+                          const float* w, const float* bias, void* out, float* bn_stats, float bn_eps, void* workspace,
+                          size_t workspace_bytes, void* stream, int h16, int out_f16) {
   LSI_REQUIRE(d && in_a && w && out && workspace, "NULL pointer argument");
+  LSI_REQUIRE(!h16 || (d->in_c_stride % 8 == 0 && (!in_b || in_b_c_stride % 8 == 0)), "fp16 activations need 8-channel-aligned pixel strides");
+  LSI_REQUIRE(!out_f16 || (d->epilogue == 0 && d->accumulate == 0 && d->c_out % 8 == 0 && d->out_c_stride % 8 == 0),
+              "fp16 output is for plain conv outputs with a multiple of 8 channels");
   LSI_REQUIRE(lsi_b200_conv2d_tc_supported(d, c_in_a), "shape not supported by the tensor-core path");
   LSI_REQUIRE(c_in_a == d->c_in || (in_b && in_b_c_stride % 4 == 0 && in_b_c_stride >= d->c_in - c_in_a), "bad second source");
   LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
@@ -496,7 +563,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
   cudaStream_t st = as_stream(stream);
 
   TcParams p;
-  p.out = out; p.bias = bias; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
+  p.out = static_cast<float*>(out); p.bias = bias; p.h16 = h16 ? 1 : 0; p.out_f16 = out_f16 ? 1 : 0; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
   const int s = d->mode == 1 ? d->stride : 1;
   p.Hp = d->h_out / s; p.Wp = d->w_out / s;
   // x-merge: unit-stride gathers with more than one tap along x, on images wide enough for 16x8 tiles to make sense
@@ -519,21 +586,28 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
   {
     const long long total = (long long)taps * p.n_pad * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    prep_weights_kernel<<<(unsigned)g, 256, 0, st>>>(w, wk, taps, d->c_in, d->c_out, p.n_pad, d->w_tap_stride, d->w_ci_stride,
-                                                     d->w_co_stride);
+    if (h16)
+      prep_weights_f16_kernel<<<(unsigned)g, 256, 0, st>>>(w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, p.n_pad,
+                                                           d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
+    else
+      prep_weights_kernel<<<(unsigned)g, 256, 0, st>>>(w, wk, taps, d->c_in, d->c_out, p.n_pad, d->w_tap_stride, d->w_ci_stride,
+                                                       d->w_co_stride);
     LSI_LAUNCH_CHECK();
   }
 
   // tensor maps
-  auto make_act_map = [&](CUtensorMap* m, const float* base, int channels, int cs) -> int {
+  const cuuint64_t eb = h16 ? 2 : 4;
+  const CUtensorMapDataType dt = h16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  const CUtensorMapSwizzle sw = h16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  auto make_act_map = [&](CUtensorMap* m, const void* base, int channels, int cs) -> int {
     const int es = (d->mode == 0) ? d->stride : 1;      // element (traversal) stride of the gather
     cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
-    cuuint64_t strides[3] = {(cuuint64_t)cs * 4, (cuuint64_t)d->w_in * cs * 4, (cuuint64_t)d->h_in * d->w_in * cs * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * eb, (cuuint64_t)d->w_in * cs * eb, (cuuint64_t)d->h_in * d->w_in * cs * eb};
     cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((kTileW - 1) * es + 1), (cuuint32_t)((kTileH - 1) * es + 1), 1};
     if (p.xm) { box[1] = (cuuint32_t)p.halo_w; box[2] = (cuuint32_t)p.th; }
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
-    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = encode(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return LSI_B200_ECUDA; }
     return LSI_B200_OK;
@@ -544,15 +618,16 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
   else map_b = map_a;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * p.n_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * eb};
     cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)p.n_tile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&map_w, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(&map_w, dt, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
-  const uint32_t b_bytes = ((uint32_t)p.n_tile * 128 + 1023) & ~1023u;
-  const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * 128 + (uint32_t)d->kw * b_bytes : kTileM * 128 + b_bytes;
+  const uint32_t rb = h16 ? 64u : 128u;
+  const uint32_t b_bytes = ((uint32_t)p.n_tile * rb + 1023) & ~1023u;
+  const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb + (uint32_t)d->kw * b_bytes : kTileM * rb + b_bytes;
   int stages = (int)((74u * 1024u) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
@@ -590,4 +665,14 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const float* in_a, int c_
     LSI_LAUNCH_CHECK();
   }
   return LSI_B200_OK;
+}
+
+// fp16 activations (in_a / in_b / out point to __half tensors, strides in elements), fp16-rounded weights, fp32 accumulation,
+// batch statistics from the fp32 accumulators: the inference-only 'f16' mode of lsi.nnutils.nets.  out_f16 == 0 writes fp32.
+extern "C" int lsi_b200_conv2d_tc_h(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
+                                    const float* w, const float* bias, void* out, int out_f16, float* bn_stats, float bn_eps,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  LSI_REQUIRE(!bn_stats || (d && d->epilogue == 0 && d->accumulate == 0), "bn statistics need a plain conv output");
+  return conv2d_tc_impl(d, in_a, c_in_a, in_b, in_b_c_stride, w, bias, out, bn_stats, bn_eps, workspace, workspace_bytes, stream, 1,
+                        out_f16);
 }

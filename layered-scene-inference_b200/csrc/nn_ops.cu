@@ -5,6 +5,8 @@
 //   sigmoid head           pixelwise_predictor's activation (nets.py:143); forward is fused into the conv epilogue
 //   Adam                   tf.train.AdamOptimizer(lr, beta1) (train_utils.py:112): m,v update with the
 //                          lr*sqrt(1-b2^t)/(1-b1^t) step and epsilon outside the square root
+#include <cuda_fp16.h>
+
 #include "capi_common.h"
 #include "common.cuh"
 
@@ -183,9 +185,71 @@ static unsigned ew_grid(long long n) {
   return (unsigned)g;
 }
 
+// fp16 activations (inference-only 'f16' mode): y(half) = relu((x - mean) * rstd + beta), x stored as half or float;
+// dense, C % 8 == 0, 8 channels per thread (128-bit half loads/stores)
+template <bool kInF16>
+__global__ void __launch_bounds__(256) bn_apply_h_kernel(const void* __restrict__ xv, const float* __restrict__ stats,
+                                                         const float* __restrict__ beta, __half* __restrict__ y, long long total8,
+                                                         unsigned c8n) {
+  // the grid-stride (gridDim.x * 256) is a multiple of c8n (a power of two <= 256 or a divisor the host checked), so a
+  // thread meets the same eight channels in every iteration: scale/shift are loop invariants in registers
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((unsigned long long)i0 % c8n) * 8;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float mean = __ldg(stats + 2 * (c + k)), rstd = __ldg(stats + 2 * (c + k) + 1);
+    sa[k] = rstd; sb[k] = fmaf(-mean, rstd, __ldg(beta + c + k));
+  }
+  for (long long i = i0; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    if (kInF16) {
+      const uint4 u = __ldcs(reinterpret_cast<const uint4*>(xv) + i);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        v[2 * k] = f.x; v[2 * k + 1] = f.y;
+      }
+    } else {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(xv) + 2 * i), b = __ldcs(reinterpret_cast<const float4*>(xv) + 2 * i + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h = __floats2half2_rn(fmaxf(fmaf(v[2 * k], sa[2 * k], sb[2 * k]), 0.f),
+                                          fmaxf(fmaf(v[2 * k + 1], sa[2 * k + 1], sb[2 * k + 1]), 0.f));
+      o[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace lsi
 
 using namespace lsi;
+
+extern "C" int lsi_b200_bn_relu_apply_h(const void* x, int x_f16, const float* beta, const float* stats, void* y, long long n_pixels,
+                                        int channels, void* stream) {
+  LSI_REQUIRE(x && beta && stats && y, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 8 && channels % 8 == 0, "channels must be a multiple of 8");
+  LSI_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)beta & 7) == 0 && ((uintptr_t)stats & 15) == 0,
+              "tensors must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const long long total8 = n_pixels * channels / 8;
+  const unsigned c8n = (unsigned)channels / 8;
+  // grid such that gridDim.x * 256 is a multiple of c8n (each thread then keeps its channels): blocks in multiples of m
+  unsigned m = c8n, g256 = 256;
+  while (g256) { const unsigned t = m % g256; m = g256; g256 = t; }   // m = gcd(c8n, 256)
+  m = c8n / m;
+  unsigned grid = ew_grid(total8);
+  grid = (grid + m - 1) / m * m;
+  if (x_f16) bn_apply_h_kernel<true><<<grid, 256, 0, st>>>(x, stats, beta, static_cast<__half*>(y), total8, c8n);
+  else bn_apply_h_kernel<false><<<grid, 256, 0, st>>>(x, stats, beta, static_cast<__half*>(y), total8, c8n);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
 
 extern "C" size_t lsi_b200_bn_workspace_bytes(int channels) {
   return (size_t)kStatBlocks * (size_t)(channels > 0 ? channels : 1) * 2 * sizeof(double);

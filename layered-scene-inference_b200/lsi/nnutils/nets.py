@@ -148,7 +148,7 @@ def _bn_workspace(device, channels):
     return _bn_ws[key]
 
 
-_CONV_MODE = 'tf32'
+_CONV_MODE = os.environ.get('LSI_B200_CONV_MODE', 'tf32')   # 'tf32' | 'fp32' | 'f16' (see set_conv_mode)
 
 
 def set_conv_mode(mode):
@@ -156,9 +156,27 @@ def set_conv_mode(mode):
     fp32 CUDA-core kernels elsewhere (the 3-channel stem, weight gradients).  'fp32': CUDA-core kernels everywhere --
     the bit-for-bit-reproducible-arithmetic mode the 1e-4 parity tests of the CNN run in."""
     global _CONV_MODE
-    if mode not in ('tf32', 'fp32'):
+    if mode not in ('tf32', 'fp32', 'f16'):
         raise ValueError(mode)
     _CONV_MODE = mode
+
+
+def _tc_mode():
+    return _CONV_MODE in ('tf32', 'f16')
+
+
+def _f16_infer():
+    """'f16': inference-only (no_grad) variant of 'tf32' in which every activation between the stem and the prediction conv
+    lives in HBM as fp16 (same 10-bit mantissa as a TF32 operand), the tensor-core kernels run kind::f16 MMAs with fp32
+    accumulation and batch statistics come from the fp32 accumulators.  With autograd enabled it behaves like 'tf32'."""
+    return _CONV_MODE == 'f16' and not torch.is_grad_enabled()
+
+
+def _dev_act(t, name):
+    """A hot-path activation: CUDA, contiguous, fp32 (or fp16 on the 'f16' inference path)."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float16 and _f16_infer():
+        return t if t.is_contiguous() else t.contiguous()
+    return _b200.dev_f32(t, name)
 
 
 def get_conv_mode():
@@ -176,7 +194,7 @@ def _tc_workspace(device, nbytes):
 
 
 def _tc_ok(d, c_in_a, *tensors):
-    return (_CONV_MODE == 'tf32' and _b200.lib().lsi_b200_conv2d_tc_supported(d, c_in_a) == 1
+    return (_tc_mode() and _b200.lib().lsi_b200_conv2d_tc_supported(d, c_in_a) == 1
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
 
 
@@ -206,7 +224,7 @@ def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=Non
 
 def _wgrad(desc_kw, big, small, dw):
     d = _b200.ConvDesc(**desc_kw)
-    if (_CONV_MODE == 'tf32' and _b200.lib().lsi_b200_conv2d_wgrad_tc_supported(d) == 1 and big.data_ptr() % 16 == 0
+    if (_tc_mode() and _b200.lib().lsi_b200_conv2d_wgrad_tc_supported(d) == 1 and big.data_ptr() % 16 == 0
             and small.data_ptr() % 16 == 0):
         _b200.call('lsi_b200_conv2d_wgrad_tc', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
         return
@@ -239,9 +257,13 @@ class _Pending(object):
 
     def materialize(self):
         z = self.z
+        B, H, W, C = z.shape
+        if z.dtype == torch.float16 and _f16_infer():
+            _b200.call('lsi_b200_bn_relu_apply_h', _b200.ptr(z), 1, _b200.ptr(self.beta), _b200.ptr(self.stats), _b200.ptr(z),
+                       B * H * W, C, _b200.stream())
+            return z
         if z.dtype != torch.float32:     # fp16-stored raw output met a consumer that cannot normalise on load
             z = z.float()
-        B, H, W, C = z.shape
         _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(self.beta), _b200.ptr(z), _b200.ptr(self.stats),
                    B * H * W, C, C, C, BN_EPS, 1, 1, _b200.ptr(_bn_workspace(z.device, C)), _b200.stream())
         return z
@@ -252,7 +274,7 @@ def _materialize(x):
 
 
 def _halo_ok(d, *tensors):
-    return (_HALO and _CONV_MODE == 'tf32' and not torch.is_grad_enabled()
+    return (_HALO and _tc_mode() and not torch.is_grad_enabled()
             and _b200.lib().lsi_b200_conv2d_halo_supported(d) == 1
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
 
@@ -415,13 +437,14 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
     Inference path (no_grad, tensor-core mode): the conv writes its RAW output and reduces the batch statistics in its
     epilogue; with defer=True the normalise + ReLU pass is left to the consumer (`_Pending`), otherwise it runs in
     place.  A `_Pending` input is normalised on load when the halo-tile kernel supports the layer."""
-    if not torch.is_grad_enabled() and _CONV_MODE == 'tf32':
+    if not torch.is_grad_enabled() and _tc_mode():
+        h = _f16_infer()
         pair = isinstance(x, (tuple, list))
         if pair:
-            a, b = (_b200.dev_f32(_materialize(t), scope + ' input') for t in x)
+            a, b = (_dev_act(_materialize(t), scope + ' input') for t in x)
             ca, cin = a.shape[3], a.shape[3] + b.shape[3]
         else:
-            a = x if isinstance(x, _Pending) else _b200.dev_f32(x, scope + ' input')
+            a = x if isinstance(x, _Pending) else _dev_act(x, scope + ' input')
             b, ca, cin = None, a.shape[3], a.shape[3]
         B, H, W = a.shape[0], a.shape[1], a.shape[2]
         geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
@@ -430,17 +453,27 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
         d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=ca))
         dev = a.device
         done = False
-        if not pair and _halo_ok(d, a.z if isinstance(a, _Pending) else a):
+        a_raw = a.z if isinstance(a, _Pending) else a
+        if not pair and _halo_ok(d, a_raw) and (a_raw.dtype == torch.float32 or isinstance(a, _Pending)):
             # the raw output of a 32-channel head layer is read by exactly one consumer, a halo-kernel conv that
             # normalises it on load and feeds fp16 MMAs: store it as fp16 (half the bytes of these byte-bound layers)
-            z_dt = torch.float16 if (defer and _HALO_F16_STORE and cout == 32) else torch.float32
+            z_dt = torch.float16 if (h or (defer and _HALO_F16_STORE and cout == 32)) else torch.float32
             z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=z_dt, device=dev)
             stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
             _conv_halo(d, a, w, z, out_stats=stats)
             done = True
         else:
             a = _materialize(a)
-            if _tc_ok(d, ca, a, b):
+            if h and _tc_ok(d, ca, a, b):
+                a, b = a.half() if a.dtype != torch.float16 else a, (b.half() if (b is not None and b.dtype != torch.float16) else b)
+                z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float16, device=dev)
+                stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
+                nws = int(_b200.lib().lsi_b200_conv2d_tc_workspace_bytes(d))
+                ws = _tc_workspace(dev, nws)
+                _b200.call('lsi_b200_conv2d_tc_h', d, _b200.ptr(a), ca, _b200.ptr(b), 0 if b is None else b.shape[-1], _b200.ptr(w),
+                           None, _b200.ptr(z), 1, _b200.ptr(stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+                done = True
+            elif _tc_ok(d, ca, a, b):
                 z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float32, device=dev)
                 stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
                 have = _conv(dict(geo.fwd, in_c_stride=ca), a, w, z, bn_stats=stats, inp_b=b, c_in_a=ca)
@@ -454,12 +487,15 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
     if isinstance(x, (tuple, list)):
         a, b = (_b200.dev_f32(t, scope + ' input') for t in x)
         x = _ConcatChannels.apply(a, b)
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float16:
+        x = x.float()
     x = _b200.dev_f32(x, scope + ' input')
     B, H, W, cin = x.shape
     geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
     w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
     beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
-    return _ConvBNReLU.apply(x, w, beta, geo)
+    y = _ConvBNReLU.apply(x, w, beta, geo)
+    return y.half() if _f16_infer() else y       # (the 3-channel stem: fp32 CUDA-core conv, handed on as fp16)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -508,7 +544,8 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
             _conv_halo(dp, feat_l, w, y, bias=b, out_scale=_out_scale)
             preds.append(y)
         else:
-            y = _ConvBiasSigmoid.apply(_materialize(feat_l), w, b, geo)
+            fm = _materialize(feat_l)
+            y = _ConvBiasSigmoid.apply(fm.float() if fm.dtype != torch.float32 else fm, w, b, geo)
             preds.append(y if _out_scale is None else y * _out_scale)
     if packed is not None and len(preds) == n_layers and all(p_.data_ptr() == packed[i].data_ptr() for i, p_ in enumerate(preds)):
         return packed, {}

@@ -152,6 +152,33 @@ def test_heads_match_generic_path():
         assert float(d.max()) < 2e-2 and float(d.mean()) < 1e-3, (float(d.max()), float(d.mean()))
 
 
+def test_f16_inference_mode_error_class():
+    """nets.set_conv_mode('f16'): every activation between the stem and the prediction conv stored as fp16, kind::f16 MMAs.
+    Measured against the fp32 CUDA-core mode, its error must be of the TF32 mode's class (one extra 2^-11 rounding per
+    layer; the 2-sample batch norms of this fixture amplify either)."""
+    from lsi.nnutils import nets
+    torch.manual_seed(0)
+    store = nets.ParamStore()
+    img = torch.rand(2, 128, 128, 3, device='cuda')
+    outs = {}
+    try:
+        for i, mode in enumerate(('fp32', 'tf32', 'f16')):
+            nets.set_conv_mode(mode)
+            with torch.no_grad():
+                _, fd, sk, _ = nets.encoder_decoder_unet(img, nl_diff_enc_dec=3, reuse=i > 0, _store=store)
+                tex, _, disp = nets.ldi_predictor(fd, n_layers=2, reuse=i > 0, n_layerwise_steps=3, skip_feat=sk, _store=store)
+            assert tex.dtype == torch.float32 and disp.dtype == torch.float32
+            outs[mode] = torch.cat([tex, disp], dim=-1).clone()
+    finally:
+        nets.set_conv_mode('tf32')
+    e_tf32 = (outs['tf32'] - outs['fp32']).abs()
+    e_f16 = (outs['f16'] - outs['fp32']).abs()
+    print('tf32 vs fp32: max %.3e mean %.3e; f16 vs fp32: max %.3e mean %.3e' % (float(e_tf32.max()), float(e_tf32.mean()),
+                                                                                float(e_f16.max()), float(e_f16.mean())))
+    assert float(e_f16.mean()) < 2.5 * float(e_tf32.mean()) + 1e-4
+    assert float(e_f16.max()) < 2.5 * float(e_tf32.max()) + 1e-3
+
+
 def test_unsupported_shapes_are_refused():
     from lsi import _b200
     lib = _b200.lib()

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-3
 
 
-def _run_both(B, Hi, Wi, Cin, Cout, k, s, mode, transposed_weights, split=None, epilogue=0, accumulate=0, seed=0):
+def _run_both(B, Hi, Wi, Cin, Cout, k, s, mode, transposed_weights, split=None, epilogue=0, accumulate=0, seed=0, h16=False,
+              out_f16=False):
     from lsi import _b200
     from lsi.nnutils.nets import same_pad
     lib = _b200.lib()
@@ -25,6 +26,8 @@ def _run_both(B, Hi, Wi, Cin, Cout, k, s, mode, transposed_weights, split=None, 
         Ho, Wo = Hi * s, Wi * s
         pt = pl = 1 if s == 2 else same_pad(Ho, k, 1)[0]
     x = torch.randn(B, Hi, Wi, Cin, device=dev)
+    if h16:                    # fp16-stored activations: the reference sees the same rounded values
+        x = x.half().float()
     if transposed_weights:     # [kh,kw,cout,cin]
         w = torch.randn(k, k, Cout, Cin, device=dev) / (k * k * Cin) ** 0.5
         ws = dict(w_tap_stride=Cin * Cout, w_ci_stride=1, w_co_stride=Cin)
@@ -43,6 +46,23 @@ def _run_both(B, Hi, Wi, Cin, Cout, k, s, mode, transposed_weights, split=None, 
     assert lib.lsi_b200_conv2d_tc_supported(d, ca) == 1
     nws = lib.lsi_b200_conv2d_tc_workspace_bytes(d)
     wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
+    if h16:
+        stats = torch.zeros(Cout, 2, device=dev) if (epilogue == 0 and not accumulate) else None
+        outh = torch.full((B, Ho, Wo, Cout), 7.0, device=dev, dtype=torch.float16) if out_f16 else out
+        if split is None:
+            _b200.call('lsi_b200_conv2d_tc_h', d, _b200.ptr(x.half()), Cin, None, 0, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(outh),
+                       int(out_f16), _b200.ptr(stats), 1e-3, _b200.ptr(wsb), nws, _b200.stream())
+        else:
+            xa, xb = x[..., :split].half().contiguous(), x[..., split:].half().contiguous()
+            d2 = _b200.ConvDesc(**dict(kw, in_c_stride=split))
+            _b200.call('lsi_b200_conv2d_tc_h', d2, _b200.ptr(xa), split, _b200.ptr(xb), Cin - split, _b200.ptr(w), _b200.ptr(bias),
+                       _b200.ptr(outh), int(out_f16), _b200.ptr(stats), 1e-3, _b200.ptr(wsb), nws, _b200.stream())
+        torch.cuda.synchronize()
+        if stats is not None:
+            mean = ref.mean(dim=(0, 1, 2)); var = ref.var(dim=(0, 1, 2), unbiased=False)
+            assert rel_err(stats[:, 0].cpu(), mean.cpu()) < TOL
+            assert rel_err(stats[:, 1].cpu(), torch.rsqrt(var + 1e-3).cpu()) < TOL
+        return outh.float(), ref
     if split is None:
         _b200.call('lsi_b200_conv2d_tc', d, _b200.ptr(x), Cin, None, 0, _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out),
                    _b200.ptr(wsb), nws, _b200.stream())
@@ -106,6 +126,26 @@ def test_upconv_phase_decomposed(B, H, W, Cin, Cout):
 def test_conv_stride2_element_strides(B, H, W, Cin, Cout, k):
     out, ref = _run_both(B, H, W, Cin, Cout, k, 2, 0, False)
     assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k,s,mode,split,out_f16', [
+    (1, 8, 16, 32, 32, 3, 1, 0, None, True),         # one tile, dense 64-byte rows
+    (2, 21, 37, 96, 64, 3, 1, 0, 64, True),          # x-merged halo rows, ragged, concat on the fly (upcnv2b)
+    (1, 16, 16, 192, 128, 3, 1, 0, 128, True),       # upcnv3b
+    (1, 16, 40, 32, 32, 7, 1, 0, None, True),        # cnv1b: 7 taps per halo row
+    (1, 48, 16, 64, 64, 5, 1, 0, None, False),       # fp32 output
+    (1, 4, 6, 1024, 512, 3, 1, 0, 512, True),        # icnv7: four N tiles
+    (2, 16, 32, 64, 128, 3, 2, 0, None, True),       # stride 2 via element strides
+    (1, 32, 64, 32, 64, 5, 2, 0, None, True),
+    (2, 19, 11, 128, 64, 4, 2, 1, None, True),       # phase-decomposed up-conv
+    (1, 5, 9, 128, 128, 4, 2, 1, None, True),
+    (1, 8, 16, 32, 4, 3, 1, 0, None, False),         # N padded to 16
+])
+def test_conv_fp16_operands(B, H, W, Cin, Cout, k, s, mode, split, out_f16):
+    """lsi_b200_conv2d_tc_h (fp16 activations and weights, fp32 accumulation, statistics from the accumulators) against the
+    fp32 kernel on the same fp16-rounded activations."""
+    out, ref = _run_both(B, H, W, Cin, Cout, k, s, mode, mode == 1, split=split, h16=True, out_f16=out_f16)
+    assert rel_err(out.cpu(), ref.cpu()) < (3e-3 if out_f16 else TOL)
 
 
 @pytest.mark.parametrize('B,H,W,Ca,Cb,k,s', [

@@ -30,6 +30,10 @@ def timed_call(name, *args):
         taps = d.kh * d.kw / (d.stride * d.stride if d.mode == 1 else 1)
         fl = 2.0 * d.batch * d.h_out * d.w_out * d.c_out * d.c_in * taps
         by = 4.0 * d.batch * (d.h_in * d.w_in * d.c_in + d.h_out * d.w_out * d.c_out)
+    elif name == 'lsi_b200_bn_relu_apply_h':
+        P, C = args[5], args[6]
+        key = 'bn_relu_apply_h P=%d C=%d' % (P, C)
+        by = (6.0 if not args[1] else 4.0) * P * C
     elif name == 'lsi_b200_bn_relu_forward':
         P, C = args[4], args[5]
         key = 'bn_relu_forward P=%d C=%d' % (P, C)
@@ -63,7 +67,7 @@ for key, e0, e1, fl, by in records:
     v = agg.setdefault(key, [0.0, 0, 0.0, 0.0])
     v[0] += e0.elapsed_time(e1); v[1] += 1; v[2] += fl; v[3] += by
 tot = sum(v[0] for v in agg.values()) / a.iters
-print('halo=%s  B=%d %dx%d L=%d: %.2f ms/step wall (events), %.2f ms summed over launches' % (nets._HALO, a.batch, a.h, a.w, a.layers, t0.elapsed_time(t1) / a.iters, tot))
+print('mode=%s halo=%s  B=%d %dx%d L=%d: %.2f ms/step wall (events), %.2f ms summed over launches' % (nets.get_conv_mode(), nets._HALO, a.batch, a.h, a.w, a.layers, t0.elapsed_time(t1) / a.iters, tot))
 print('%-72s %5s %9s %8s %9s' % ('call', 'n', 'ms/step', 'TFLOP/s', 'alg GB/s'))
 for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     ms = v[0] / a.iters
