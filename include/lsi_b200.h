@@ -218,6 +218,15 @@ LSI_B200_API int lsi_b200_conv2d_tc_h(const lsi_b200_conv_desc* d, const void* i
                                       int in_b_c_stride, const float* w, const float* bias, void* out, int out_f16,
                                       float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tensor-core stem (nets.py:273, cnv1: 7x7 stride-2 conv, 3 -> 32 channels, fp32 NHWC input with 12-byte pixels that TMA
+ * cannot address): im2col built by the threads in shared memory (fp16, 64B swizzle), kind::f16 tcgen05 MMAs, fp32
+ * accumulation; out is __half (out_f16 != 0) or float; bn_stats (optional) = (mean, rsqrt(biased var + eps)) of the raw
+ * output.  Same descriptor semantics as lsi_b200_conv2d. */
+LSI_B200_API int lsi_b200_conv2d_stem_tc_supported(const lsi_b200_conv_desc* d);
+LSI_B200_API size_t lsi_b200_conv2d_stem_tc_workspace_bytes(void);
+LSI_B200_API int lsi_b200_conv2d_stem_tc(const lsi_b200_conv_desc* d, const float* in, const float* w, void* out, int out_f16,
+                                         float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
+
 /* y (__half, dense [n_pixels, channels]) = relu((x - mean) * rstd + beta) with given stats[c] = (mean, rstd); x is __half
  * (x_f16 != 0) or float; channels % 8 == 0.  The normalise pass of the fp16 mode (slim.batch_norm + ReLU, nets.py:263-272). */
 LSI_B200_API int lsi_b200_bn_relu_apply_h(const void* x, int x_f16, const float* beta, const float* stats, void* y,

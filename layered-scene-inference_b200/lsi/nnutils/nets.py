@@ -233,6 +233,7 @@ def _wgrad(desc_kw, big, small, dw):
 
 _HALO = os.environ.get('LSI_B200_CONV_HALO', '1') != '0'
 _HALO_F16_STORE = os.environ.get('LSI_B200_HALO_F16_STORE', '1') != '0'
+_STEM_TC = os.environ.get('LSI_B200_STEM_TC', '1') != '0'
 _OUT_SCALE_CACHE = {}
 
 
@@ -472,6 +473,16 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
                 ws = _tc_workspace(dev, nws)
                 _b200.call('lsi_b200_conv2d_tc_h', d, _b200.ptr(a), ca, _b200.ptr(b), 0 if b is None else b.shape[-1], _b200.ptr(w),
                            None, _b200.ptr(z), 1, _b200.ptr(stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+                done = True
+            elif (h and not pair and a.dtype == torch.float32 and _STEM_TC
+                  and _b200.lib().lsi_b200_conv2d_stem_tc_supported(d) == 1):
+                # the 3-channel stem on tensor cores (im2col built in shared memory), raw fp16 output + statistics
+                z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float16, device=dev)
+                stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
+                nws = int(_b200.lib().lsi_b200_conv2d_stem_tc_workspace_bytes())
+                ws = _tc_workspace(dev, nws)
+                _b200.call('lsi_b200_conv2d_stem_tc', d, _b200.ptr(a), _b200.ptr(w), _b200.ptr(z), 1, _b200.ptr(stats), BN_EPS,
+                           _b200.ptr(ws), ws.numel(), _b200.stream())
                 done = True
             elif _tc_ok(d, ca, a, b):
                 z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=torch.float32, device=dev)

@@ -180,3 +180,34 @@ def test_wgrad_tensor_core(B, H, W, Ca, Cb, k, s):
     _b200.call('lsi_b200_conv2d_wgrad_tc', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(out), _b200.stream())
     torch.cuda.synchronize()
     assert rel_err(out.cpu(), ref.cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,out_f16', [(1, 4, 128, True), (2, 37, 150, True), (1, 64, 256, False), (3, 128, 128, True)])
+def test_stem_tensor_core(B, H, W, out_f16):
+    """lsi_b200_conv2d_stem_tc (7x7 stride-2 conv 3 -> 32, im2col built in shared memory, kind::f16 MMAs) against the fp32
+    direct kernel, statistics included; ragged sizes exercise the zero-filled staging and partial tiles."""
+    from lsi import _b200
+    from lsi.nnutils.nets import same_pad
+    torch.manual_seed(B * 1000 + H + W)
+    dev = 'cuda'
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    x = torch.rand(B, H, W, 3, device=dev)
+    w = torch.randn(7, 7, 3, 32, device=dev) / 147 ** 0.5
+    d = _b200.ConvDesc(batch=B, h_in=H, w_in=W, c_in=3, h_out=Ho, w_out=Wo, c_out=32, kh=7, kw=7, stride=2, pad_top=same_pad(H, 7, 2)[0],
+                       pad_left=same_pad(W, 7, 2)[0], mode=0, w_tap_stride=96, w_ci_stride=32, w_co_stride=1, in_c_stride=3,
+                       out_c_stride=32, epilogue=0, accumulate=0)
+    ref = torch.zeros(B, Ho, Wo, 32, device=dev)
+    _b200.call('lsi_b200_conv2d', d, _b200.ptr(x), _b200.ptr(w), None, _b200.ptr(ref), _b200.stream())
+    assert _b200.lib().lsi_b200_conv2d_stem_tc_supported(d) == 1
+    out = torch.full((B, Ho, Wo, 32), 7.0, device=dev, dtype=torch.float16 if out_f16 else torch.float32)
+    st = torch.zeros(32, 2, device=dev)
+    nws = _b200.lib().lsi_b200_conv2d_stem_tc_workspace_bytes()
+    wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
+    for _ in range(2):     # twice: persistent state (barrier phases, TMEM) is per launch
+        _b200.call('lsi_b200_conv2d_stem_tc', d, _b200.ptr(x), _b200.ptr(w), _b200.ptr(out), int(out_f16), _b200.ptr(st), 1e-3,
+                   _b200.ptr(wsb), nws, _b200.stream())
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref.cpu()) < (3e-3 if out_f16 else TOL)
+    mean = ref.mean(dim=(0, 1, 2)); var = ref.var(dim=(0, 1, 2), unbiased=False)
+    assert rel_err(st[:, 0].cpu(), mean.cpu()) < TOL
+    assert rel_err(st[:, 1].cpu(), torch.rsqrt(var + 1e-3).cpu()) < TOL
