@@ -32,6 +32,7 @@ import torch
 H, W, L, B_PER_GPU = 256, 832, 4, 64
 MAX_DISP, BG_DISP, ZBUF_SCALE, DS = 0.4, 1e-3, 50.0, 1.0      # kitti constants, ldi_enc_dec.py:421-425
 METRIC = 'rendered views/sec at 256x832x4-layer'
+NCU_SPLAT_DRAM_BYTES_PER_VIEW = (238.452736e6 + 10.389248e6) / 14     # profiles/r1_splat_stream_ncu_summary.txt
 WORKLOAD = ('KITTI-like 256x832 image -> encoder-decoder U-Net + 4 LDI heads (W zero-padded to 896 for the U-Net, '
             'prediction cropped; tcgen05 convs with fp16 operands/activations and fp32 accumulation, batch-stat BN) -> forward_splat(compose_layers=True, '
             'trg_downsampling=1) -> rendered target view; batch %d per GPU' % B_PER_GPU)
@@ -265,7 +266,12 @@ def main():
     achieved = splat_bytes_per_step / (splat_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': 'splat_fwd_stream_kernel (forward splat; %d launches per step)' % (kn[0] // args.steps),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
-                'traffic': None, 'algorithmic_bytes_per_step': splat_bytes_per_step, 'kernel_ms_per_step': splat_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (14 views) in profiles/r1_splat_stream_ncu_summary.txt,
+                # scaled to the views of one launch here; ncu flushes L2 before each replay, so the 3.4 MB/view accumulator that
+                # is L2-resident in a real run (memset just before) is re-fetched and shows up as extra reads
+                'traffic': NCU_SPLAT_DRAM_BYTES_PER_VIEW * B / max(kn[0] // args.steps, 1),
+                'algorithmic_bytes_per_launch': splat_bytes_per_step / max(kn[0] // args.steps, 1),
+                'algorithmic_bytes_per_step': splat_bytes_per_step, 'kernel_ms_per_step': splat_ms,
                 'normalize_ms_per_step': kms[1] / args.steps}
     wp = -(-W // 128) * 128
     conv_flops = (21.8e9 + 23.0e9 * L) * (H * wp) / (256.0 * 768.0) * B      # forward 2*MAC per step

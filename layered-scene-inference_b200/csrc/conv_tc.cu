@@ -24,7 +24,7 @@ namespace lsi {
 
 constexpr int kTileH = 8, kTileW = 16, kTileM = kTileH * kTileW;   // 128 output pixels = 128 TMEM lanes
 constexpr int kKC = 32;                                            // fp32 channels per K chunk = one 128-byte row
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 
 struct TcParams {
@@ -628,8 +628,13 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   const uint32_t rb = h16 ? 64u : 128u;
   const uint32_t b_bytes = ((uint32_t)p.n_tile * rb + 1023) & ~1023u;
   const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb + (uint32_t)d->kw * b_bytes : kTileM * rb + b_bytes;
-  int stages = (int)((74u * 1024u) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
+  p.batch = d->batch;
+  p.total_tiles = p.tiles_x * p.tiles_y * d->batch * (p.n_pad / p.n_tile) * s * s;
+  // ring depth: 74 KB of stages (up to 4) lets 2-3 CTAs share an SM; the small-spatial layers of the trunk (fewer tiles than
+  // SMs, K = 9 x 512 .. 1024) are one long TMA -> MMA latency chain per CTA, so they get the whole SM: up to 8 stages
+  const bool latency_bound = p.total_tiles <= num_sms();
+  int stages = (int)(((latency_bound ? 200u : 74u) * 1024u) / stage_bytes);
+  if (stages > (latency_bound ? kMaxStages : 4)) stages = latency_bound ? kMaxStages : 4;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + (bn_stats ? 4 * 32 * 33 * sizeof(float) : 0);
@@ -638,8 +643,6 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
     LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  p.batch = d->batch;
-  p.total_tiles = p.tiles_x * p.tiles_y * d->batch * (p.n_pad / p.n_tile) * s * s;
   int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
   const int tmem_per_cta = 2 * (p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256);
   if (ctas_per_sm > 512 / tmem_per_cta) ctas_per_sm = 512 / tmem_per_cta;
