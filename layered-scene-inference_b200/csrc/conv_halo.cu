@@ -24,6 +24,14 @@
 #include "common.cuh"
 
 namespace lsi {
+
+// mbarrier.try_wait suspend-time hint: a waiting thread sleeps until the phase completes (or this many ns pass) instead
+// of re-polling -- in the halo kernel 27 % of all issued instructions were YIELD/TRYWAIT/BRA of waiting warps
+#ifndef LSI_SUSPEND_HINT_DEFINED
+#define LSI_SUSPEND_HINT_DEFINED
+constexpr unsigned kSuspendHintNs = 0x989680u;
+#endif
+
 namespace {
 
 constexpr int kTH = 16, kTW = 8, kTileM = kTH * kTW;   // 128 output pixels = 128 TMEM lanes
@@ -31,6 +39,7 @@ constexpr int kKC = 32;                                // fp32 channels per 128-
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;                          // warp 0 TMA, 1 MMA, 2-5 epilogue, 6-9 transform
 constexpr int kThreadsWide = 448;                      // 1-CTA/SM variant: 8 transform warps (6-13)
+constexpr int kThreadsAll = 576;                       // all-phase variant: 8 epilogue warps (2-9, two per TMEM lane group), 8 transform warps (10-17)
 constexpr int kStgPitch = 36;                          // floats per staged pixel (144 B: conflict-free 128-bit rows)
 constexpr int kMaxCin = 128;
 
@@ -46,6 +55,8 @@ struct HaloParams {
   int in_f16;                // 1: the input tensor is stored as fp16 (RAW output of a producer run with out_f16): 64-byte rows,
                              //    64B swizzle, normalised in place by the transform warps (implies f16)
   int out_f16;               // 1: the RAW output is stored as fp16 (its only consumer normalises on load and feeds fp16 MMAs anyway)
+  int all_phase;             // 1 (kAll): one CTA computes all stride^2 output phases of an up-conv tile from ONE halo load/transform
+  int oy_min, ox_min;        // kAll: halo origin relative to the tile origin (minimum over the phases)
   int halo_w, halo_h;
   uint32_t halo_bytes, b_tap_bytes, w_bytes, div_halo_w;
 };
@@ -65,11 +76,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -253,9 +264,24 @@ __device__ __forceinline__ void transform_tile_h(uint4* tile, const float* bn_a,
   }
 }
 
+// tap list and halo offset of output phase (py, px) of a stride-s gather in mode 1 (see the phase setup in the kernel)
+struct PhaseGeom { int ky0, kx0, nky, nkx, oy_off, ox_off; };
+__device__ __forceinline__ PhaseGeom phase_geom(const HaloParams& p, int s, int py, int px) {
+  PhaseGeom g;
+  g.ky0 = (py + p.pad_t) % s; g.kx0 = (px + p.pad_l) % s;
+  g.nky = (p.kh - g.ky0 + s - 1) / s; g.nkx = (p.kw - g.kx0 + s - 1) / s;
+  g.oy_off = (py + p.pad_t - (g.ky0 + (g.nky - 1) * s)) / s;
+  g.ox_off = (px + p.pad_l - (g.kx0 + (g.nkx - 1) * s)) / s;
+  return g;
+}
+
 // kWide: n_tile == 64 (two 32-column passes per accumulator, two sets of statistics registers)
-template <bool kWide>
-__global__ void __launch_bounds__(kWide ? kThreadsWide : kThreads, kWide ? 1 : 2)
+// kAll:  n_tile == 32 up-conv whose stride^2 output phases are all computed by the same CTA: the halo tile is loaded and
+//        normalised once instead of once per phase (that redundancy was ~45 % of the shared-memory traffic of upcnv1);
+//        the whole 16-tap filter bank is resident, one 32-column accumulator per phase.  Like kWide it runs one CTA per SM
+//        with 8 transform warps.
+template <bool kWide, bool kAll>
+__global__ void __launch_bounds__(kAll ? kThreadsAll : (kWide ? kThreadsWide : kThreads), (kWide || kAll) ? 1 : 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
@@ -279,25 +305,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const bool bn_in = p.in_stats != nullptr;
 
   // phase of this CTA (up-conv / data-gradient mode: one of stride^2 output phases; plain conv: the only one)
+  constexpr bool kBig = kWide || kAll;
   const int s = (p.mode == 1) ? p.stride : 1;
-  const int G = s * s;
+  const int G = kAll ? 1 : s * s;
+  const int n_ph = kAll ? s * s : 1;           // phases computed per tile by this CTA
   const int phase = (int)(blockIdx.x % G);
   const int cta_in_group = (int)(blockIdx.x / G), ctas_per_group = (int)(gridDim.x / G);
   const int py = phase / s, px = phase % s;
   const int ky0 = (p.mode == 1) ? ((py + p.pad_t) % s) : 0, kx0 = (p.mode == 1) ? ((px + p.pad_l) % s) : 0;
   const int nky = (p.kh - ky0 + s - 1) / s, nkx = (p.kw - kx0 + s - 1) / s;
   // halo origin relative to the tile origin, in source pixels (exact divisions: the tap list matches the phase)
-  const int oy_off = (p.mode == 0) ? -p.pad_t : (py + p.pad_t - (ky0 + (nky - 1) * s)) / s;
-  const int ox_off = (p.mode == 0) ? -p.pad_l : (px + p.pad_l - (kx0 + (nkx - 1) * s)) / s;
+  const int oy_off = kAll ? p.oy_min : ((p.mode == 0) ? -p.pad_t : (py + p.pad_t - (ky0 + (nky - 1) * s)) / s);
+  const int ox_off = kAll ? p.ox_min : ((p.mode == 0) ? -p.pad_l : (px + p.pad_l - (kx0 + (nkx - 1) * s)) / s);
 
-  const uint32_t acc_cols = p.n_tile <= 32 ? 32u : (p.n_tile <= 64 ? 64u : 128u);
+  const uint32_t acc_cols = kAll ? 32u * (uint32_t)(s * s) : (p.n_tile <= 32 ? 32u : (p.n_tile <= 64 ? 64u : 128u));
   const uint32_t tmem_cols = acc_cols * 2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&xready[i], kWide ? 8 : 4); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&xready[i], kBig ? 8 : 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kAll ? 256 : 128); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -319,12 +347,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       // ---------------- TMA producer ----------------
-      mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)p.n_tile * (p.f16 ? 64u : 128u));
-      for (int i = 0; i < nky; ++i)
-        for (int j = 0; j < nkx; ++j)
+      if (kAll) {   // the whole filter bank, indexed by (ky * kw + kx)
+        mbar_expect_tx(wfull, (uint32_t)(p.kh * p.kw * p.chunks) * (uint32_t)p.n_tile * (p.f16 ? 64u : 128u));
+        for (int t = 0; t < p.kh * p.kw; ++t)
           for (int ch = 0; ch < p.chunks; ++ch)
-            tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
-                        ((ky0 + i * s) * p.kw + (kx0 + j * s)) * p.n_tile);
+            tma_load_2d(smem_u32(s_w) + (uint32_t)(t * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC, t * p.n_tile);
+      } else {
+        mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)p.n_tile * (p.f16 ? 64u : 128u));
+        for (int i = 0; i < nky; ++i)
+          for (int j = 0; j < nkx; ++j)
+            for (int ch = 0; ch < p.chunks; ++ch)
+              tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
+                          ((ky0 + i * s) * p.kw + (kx0 + j * s)) * p.n_tile);
+      }
       Ring r(p.stages);
       const uint32_t tx = (uint32_t)(p.halo_w * p.halo_h) * (p.in_f16 ? 64u : 128u);
       TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
@@ -351,6 +386,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint64_t hi_b = p.f16 ? umma_desc_hi_sw64() : umma_desc_hi(1024u);
       mbar_wait(wfull, 0);
       const uint64_t b_desc0 = umma_desc(hi_b, smem_u32(s_w));
+      // kAll (4x4 stride-2 up-conv: 4 phases x 2x2 taps): descriptor offsets of every (phase, tap) once, in registers -- the
+      // issuing thread is a single dependent instruction stream, per-tile integer divisions would dominate it
+      uint32_t a_off[16], b_off[16];
+      if (kAll) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+          const PhaseGeom g = phase_geom(p, s, ph >> 1, ph & 1);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int i = t >> 1, j = t & 1;
+            const int dy = g.oy_off - p.oy_min + g.nky - 1 - i, dx = g.ox_off - p.ox_min + g.nkx - 1 - j;
+            a_off[ph * 4 + t] = ((uint32_t)(dy * p.halo_w + dx) * row_b) >> 4;
+            b_off[ph * 4 + t] = ((uint32_t)(((g.ky0 + i * s) * p.kw + (g.kx0 + j * s)) * p.chunks) * p.b_tap_bytes) >> 4;
+          }
+        }
+      }
       Ring r(p.stages);
       int tcount = 0;
       for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ++tcount) {
@@ -364,38 +415,66 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           // descriptors advance by adding byte offsets >> 4 to the start-address field (no carry out of its 14 bits:
           // every operand lives below 256 KB)
           const uint64_t a_desc0 = umma_desc(hi_a, smem_u32(s_a) + (uint32_t)r.st * stage_bytes);
-          for (int i = 0; i < nky; ++i) {
-            const int dy = (p.mode == 0) ? i : nky - 1 - i;
-            for (int j = 0; j < nkx; ++j) {
-              const int dx = (p.mode == 0) ? j : nkx - 1 - j;
-              const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * row_b) >> 4);
-              const uint64_t bd = b_desc0 + (uint64_t)(((uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes) >> 4);
-              if (p.f16) {
+          if (kAll) {                               // every output phase from the same (normalised) halo tile
+            const uint32_t ch_off = ((uint32_t)ch * p.b_tap_bytes) >> 4;
 #pragma unroll
-                for (int kk = 0; kk < kKC / 16; ++kk) {  // UMMA K = 16 for fp16: 32 bytes along the row
-                  umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
-                  acc = 1;
-                }
-              } else {
+            for (int ph = 0; ph < 4; ++ph) {
 #pragma unroll
-                for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
-                  umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
-                  acc = 1;
+              for (int t = 0; t < 4; ++t) {
+                const uint64_t ad = a_desc0 + (uint64_t)a_off[ph * 4 + t], bd = b_desc0 + (uint64_t)(b_off[ph * 4 + t] + ch_off);
+#pragma unroll
+                for (int kk = 0; kk < kKC / 16; ++kk)
+                  umma_f16(tmem_d + (uint32_t)ph * 32u, ad + 2 * kk, bd + 2 * kk, idesc, (uint32_t)((ch | t | kk) != 0));
+              }
+            }
+            umma_commit(&empty[r.st]);
+            continue;
+          }
+          for (int ph = 0; ph < n_ph; ++ph) {
+            int g_ky0 = ky0, g_kx0 = kx0, g_nky = nky, g_nkx = nkx, base_y = 0, base_x = 0;
+            if (kAll) {
+              const PhaseGeom g = phase_geom(p, s, ph / s, ph % s);
+              g_ky0 = g.ky0; g_kx0 = g.kx0; g_nky = g.nky; g_nkx = g.nkx; base_y = g.oy_off - p.oy_min; base_x = g.ox_off - p.ox_min;
+            }
+            const uint32_t tmem_ph = tmem_d + (uint32_t)ph * 32u;
+            uint32_t acc_ph = kAll ? (uint32_t)(ch != 0) : acc;
+            for (int i = 0; i < g_nky; ++i) {
+              const int dy = (p.mode == 0) ? i : base_y + g_nky - 1 - i;
+              for (int j = 0; j < g_nkx; ++j) {
+                const int dx = (p.mode == 0) ? j : base_x + g_nkx - 1 - j;
+                const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * row_b) >> 4);
+                const uint32_t w_idx = kAll ? (uint32_t)(((g_ky0 + i * s) * p.kw + (g_kx0 + j * s)) * p.chunks + ch)
+                                            : (uint32_t)((i * g_nkx + j) * p.chunks + ch);
+                const uint64_t bd = b_desc0 + (uint64_t)((w_idx * p.b_tap_bytes) >> 4);
+                if (p.f16) {
+#pragma unroll
+                  for (int kk = 0; kk < kKC / 16; ++kk) {  // UMMA K = 16 for fp16: 32 bytes along the row
+                    umma_f16(tmem_ph, ad + 2 * kk, bd + 2 * kk, idesc, acc_ph);
+                    acc_ph = 1;
+                  }
+                } else {
+#pragma unroll
+                  for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
+                    umma_tf32(tmem_ph, ad + 2 * kk, bd + 2 * kk, idesc, acc_ph);
+                    acc_ph = 1;
+                  }
                 }
               }
             }
+            if (!kAll) acc = acc_ph;
           }
           umma_commit(&empty[r.st]);               // frees the stage once these MMAs have read it
         }
         umma_commit(&tmem_full[buf]);              // accumulator complete
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < (kAll ? 10 : 6)) {
     // ---------------- epilogue: TMEM -> registers -> staging -> global ----------------
     const int lg = warp & 3;                     // TMEM lane group this warp may access
+    const int eset = kAll ? ((warp - 2) >> 2) : 0;   // kAll: two warps per lane group, each takes every other phase
     const int row = lg * 32 + lane;              // A-tile row = pixel within the 16 x 8 patch
     const int hy = row >> 3, wx = row & 7;
-    float* stg = staging + (size_t)lg * 32 * kStgPitch;
+    float* stg = staging + (size_t)(eset * 4 + lg) * 32 * kStgPitch;
     // batch statistics: lane (q4, c4) meets channels cc + c4 .. c4 + 3 of pixels q4, q4 + 4, ... in the store loop below and
     // sums them there (zero rows for pixels outside the output), so the statistics cost no extra shared-memory reads
     float4 ssum0 = make_float4(0.f, 0.f, 0.f, 0.f), ssum1 = ssum0, ssq0 = ssum0, ssq1 = ssum0;   // channels cc = 0 / cc = 32
@@ -408,9 +487,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool in_range = (y0 + hy) < p.Hp && (x0 + wx) < p.Wp;
+      for (int ph = eset; ph < n_ph; ph += (kAll ? 2 : 1)) {   // kAll: one 32-column accumulator per output phase
+      const int e_py = kAll ? ph / s : py, e_px = kAll ? ph % s : px;
       for (int cc = 0; cc < (kWide ? 64 : p.n_tile); cc += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc + (kAll ? (uint32_t)ph * 32u : 0u);
         if (p.n_tile - cc >= 32) {
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -430,14 +511,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int j = 16; j < 32; ++j) r[j] = 0u;
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cc + 32 >= p.n_tile) {               // last read of this accumulator: hand the buffer back to the MMA issuer
+        if (cc + 32 >= p.n_tile && ph + (kAll ? 2 : 1) >= n_ph) {   // this warp's last read of the accumulator: hand the buffer back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty[buf]);
         }
         if (direct4) {
           if (in_range) {
             int oy = y0 + hy, ox = x0 + wx;
-            if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
+            if (p.mode == 1) { oy = oy * s + e_py; ox = ox * s + e_px; }
             float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -479,7 +560,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           sa.x += v.x; sa.y += v.y; sa.z += v.z; sa.w += v.w;
           sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
           if (oy < p.Hp && ox < p.Wp) {
-            if (p.mode == 1) { oy = oy * s + py; ox = ox * s + px; }
+            if (p.mode == 1) { oy = oy * s + e_py; ox = ox * s + e_px; }
             const size_t e = ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4;
             if (p.out_f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + e) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
             else *reinterpret_cast<float4*>(p.out + e) = v;
@@ -493,9 +574,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ssq1.x += sq.x; ssq1.y += sq.y; ssq1.z += sq.z; ssq1.w += sq.w;
         }
       }
+      }
     }
     if (p.stat_part) {
-      float* my_part = p.stat_part + ((size_t)blockIdx.x * 4 + lg) * p.n_tile * 2;
+      float* my_part = p.stat_part + ((size_t)blockIdx.x * (kAll ? 8 : 4) + eset * 4 + lg) * p.n_tile * 2;
 #pragma unroll
       for (int i = 0; i < (kWide ? 2 : 1); ++i) {
         const float4 fs = i ? ssum1 : ssum0, fq = i ? ssq1 : ssq0;
@@ -514,7 +596,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (bn_in) {
     // ---------------- transform: producer's batch-norm + ReLU applied to the halo tile in shared memory ----------------
-    const int tid = threadIdx.x - 192;
+    const int tid = threadIdx.x - (kAll ? 320 : 192);
     Ring r(p.stages);
     TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
     for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ti.next()) {
@@ -524,7 +606,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&full[r.st], r.ph);
         float4* tile = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes);
         const float* ta = bn_a + ch * kKC; const float* tb = bn_b + ch * kKC;
-        constexpr int kNT = kWide ? 256 : 128;
+        constexpr int kNT = kBig ? 256 : 128;
         if (p.in_f16) {
           if (interior) transform_tile_h<true, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
           else transform_tile_h<false, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
@@ -614,13 +696,15 @@ EncodeTiledFn halo_get_encode() {
 
 // shared-memory plan of one launch; returns false when the layer does not fit
 struct HaloPlan {
+  int all_phase, oy_min, ox_min;
   int n_tile, chunks, nky_max, nkx_max, halo_w, halo_h, stages, ctas_per_sm;
   uint32_t halo_bytes, b_tap_bytes, w_bytes;
   size_t smem;
 };
 
-bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool in_f16 = false) {
+bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool in_f16 = false, bool all_phase = false) {
   if (!d) return false;
+  pl->all_phase = 0; pl->oy_min = 0; pl->ox_min = 0;
   if (d->c_in % kKC != 0 || d->c_in > kMaxCin || d->c_in < kKC) return false;
   if (d->mode != 0 && d->mode != 1) return false;
   if (d->mode == 0 && d->stride != 1) return false;
@@ -635,16 +719,34 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool
   pl->nky_max = (d->kh + s - 1) / s; pl->nkx_max = (d->kw + s - 1) / s;
   if (pl->nky_max * pl->nkx_max > 9) return false;
   pl->halo_w = kTW + pl->nkx_max - 1; pl->halo_h = kTH + pl->nky_max - 1;
+  int w_taps = pl->nky_max * pl->nkx_max;
+  if (all_phase) {
+    // one CTA computes every output phase: the halo is the union of the phases' windows, the whole filter bank is resident
+    if (!(d->mode == 1 && s == 2 && f16 && !small_out && d->c_out == 32)) return false;
+    int y_lo = 1 << 30, y_hi = -(1 << 30), x_lo = 1 << 30, x_hi = -(1 << 30);
+    for (int ph = 0; ph < s * s; ++ph) {
+      const int py = ph / s, px = ph % s;
+      const int ky0 = (py + d->pad_top) % s, kx0 = (px + d->pad_left) % s;
+      const int nky = (d->kh - ky0 + s - 1) / s, nkx = (d->kw - kx0 + s - 1) / s;
+      const int oy = (py + d->pad_top - (ky0 + (nky - 1) * s)) / s, ox = (px + d->pad_left - (kx0 + (nkx - 1) * s)) / s;
+      if ((py + d->pad_top - (ky0 + (nky - 1) * s)) % s || (px + d->pad_left - (kx0 + (nkx - 1) * s)) % s) return false;
+      y_lo = oy < y_lo ? oy : y_lo; y_hi = oy + nky - 1 > y_hi ? oy + nky - 1 : y_hi;
+      x_lo = ox < x_lo ? ox : x_lo; x_hi = ox + nkx - 1 > x_hi ? ox + nkx - 1 : x_hi;
+    }
+    pl->all_phase = 1; pl->oy_min = y_lo; pl->ox_min = x_lo;
+    pl->halo_h = kTH + (y_hi - y_lo); pl->halo_w = kTW + (x_hi - x_lo);
+    w_taps = d->kh * d->kw;
+  }
   pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * (in_f16 ? 64u : 128u) + 1023u) & ~1023u;
   pl->b_tap_bytes = ((uint32_t)pl->n_tile * (f16 ? 64u : 128u) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows
-  pl->w_bytes = (uint32_t)(pl->nky_max * pl->nkx_max * pl->chunks) * pl->b_tap_bytes;
-  const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + 4 * 32 * kStgPitch * sizeof(float);
+  pl->w_bytes = (uint32_t)(w_taps * pl->chunks) * pl->b_tap_bytes;
+  const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + (all_phase ? 8 : 4) * 32 * kStgPitch * sizeof(float);
   const size_t stage = (size_t)pl->halo_bytes;   // one 32-channel chunk of one tile's halo
   const size_t budget2 = 112 * 1024, budget1 = 224 * 1024;
   static int force_ctas = -1, max_stages = -1;   // measurement knobs
   if (force_ctas < 0) { const char* e = getenv("LSI_B200_HALO_CTAS"); force_ctas = e ? atoi(e) : 0; }
   if (max_stages < 0) { const char* e = getenv("LSI_B200_HALO_STAGES"); max_stages = e ? atoi(e) : 0; }
-  if (force_ctas != 1 && pl->n_tile <= 32 && fixed + 2 * stage <= budget2) {   // the 64-column variant is built for 1 CTA/SM
+  if (force_ctas != 1 && !all_phase && pl->n_tile <= 32 && fixed + 2 * stage <= budget2) {   // the 64-column / all-phase variants are built for 1 CTA/SM
     pl->ctas_per_sm = 2;
     pl->stages = (int)((budget2 - fixed) / stage);
   } else if (fixed + 2 * stage <= budget1) {
@@ -693,6 +795,12 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
   if (f16_on < 0) { const char* e = getenv("LSI_B200_HALO_F16"); f16_on = (e && atoi(e) == 0) ? 0 : 1; }
   const bool f16 = in_bn_stats != nullptr && (f16_on == 1 || in_f16);
   if (f16) { LSI_REQUIRE(halo_plan(d, &pl, true, in_f16 != 0), "halo plan (fp16) failed"); }
+  static int all_on = -1;
+  if (all_on < 0) { const char* e = getenv("LSI_B200_HALO_ALLPHASE"); all_on = (e && atoi(e) == 0) ? 0 : 1; }
+  if (f16 && all_on == 1) {   // 32-channel up-conv (upcnv1): all output phases from one halo load + transform
+    HaloPlan pa;
+    if (halo_plan(d, &pa, true, in_f16 != 0, true) && pa.stages >= 2 * pa.chunks) pl = pa;
+  }
   LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
   LSI_REQUIRE(!out_bn_stats || (d->epilogue == 0 && pl.n_tile == d->c_out), "bn statistics need a plain 32/64-channel conv output");
   LSI_REQUIRE(workspace_bytes >= lsi_b200_conv2d_halo_workspace_bytes(d), "workspace too small");
@@ -713,6 +821,7 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
   p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
   p.chunks = pl.chunks; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
   p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0; p.in_f16 = in_f16 ? 1 : 0; p.out_f16 = out_f16 ? 1 : 0;
+  p.all_phase = pl.all_phase; p.oy_min = pl.oy_min; p.ox_min = pl.ox_min;
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
   p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
 
@@ -754,13 +863,15 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
   const bool wide = pl.n_tile > 32;
-  static size_t smem_set[2] = {0, 0};
-  if (pl.smem > smem_set[wide]) {
-    if (wide) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    else LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    smem_set[wide] = pl.smem;
+  const int kv = pl.all_phase ? 2 : (wide ? 1 : 0);
+  static size_t smem_set[3] = {0, 0, 0};
+  if (pl.smem > smem_set[kv]) {
+    if (kv == 2) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else if (kv == 1) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    smem_set[kv] = pl.smem;
   }
-  const int G = s * s;
+  const int G = pl.all_phase ? 1 : s * s;
   int n_ctas = halo_num_sms() * pl.ctas_per_sm;
   if (n_ctas > p.spatial_tiles * G) n_ctas = p.spatial_tiles * G;
   n_ctas = n_ctas / G * G;
@@ -771,12 +882,13 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
   }
   {
     ScopedTiming tm(kConvTc, st);
-    if (wide) conv_halo_kernel<true><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_w, p);
-    else conv_halo_kernel<false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_w, p);
+    if (kv == 2) conv_halo_kernel<false, true><<<dim3((unsigned)n_ctas), kThreadsAll, pl.smem, st>>>(map_a, map_w, p);
+    else if (kv == 1) conv_halo_kernel<true, false><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_w, p);
+    else conv_halo_kernel<false, false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_w, p);
   }
   LSI_LAUNCH_CHECK();
   if (out_bn_stats) {
-    halo_finalize_stats_kernel<<<(d->c_out + 7) / 8, 256, 0, st>>>(p.stat_part, n_ctas * 4, pl.n_tile, d->c_out,
+    halo_finalize_stats_kernel<<<(d->c_out + 7) / 8, 256, 0, st>>>(p.stat_part, n_ctas * (pl.all_phase ? 8 : 4), pl.n_tile, d->c_out,
                                                                   (long long)d->batch * d->h_out * d->w_out, bn_eps, out_bn_stats);
     LSI_LAUNCH_CHECK();
   }
