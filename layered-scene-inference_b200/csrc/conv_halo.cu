@@ -402,6 +402,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+      // single-phase path: the same, for the <= 9 taps of this CTA's phase
+      uint32_t a_tap[9], b_tap[9];
+      const int ntaps = nky * nkx;
+      if (!kAll) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int i = t / nkx, j = t - i * nkx;
+          const int dy = (p.mode == 0) ? i : nky - 1 - i, dx = (p.mode == 0) ? j : nkx - 1 - j;
+          a_tap[t] = ((uint32_t)(dy * p.halo_w + dx) * row_b) >> 4;
+          b_tap[t] = ((uint32_t)(t * p.chunks) * p.b_tap_bytes) >> 4;
+        }
+      }
       Ring r(p.stages);
       int tcount = 0;
       for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ++tcount) {
@@ -430,38 +442,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             umma_commit(&empty[r.st]);
             continue;
           }
-          for (int ph = 0; ph < n_ph; ++ph) {
-            int g_ky0 = ky0, g_kx0 = kx0, g_nky = nky, g_nkx = nkx, base_y = 0, base_x = 0;
-            if (kAll) {
-              const PhaseGeom g = phase_geom(p, s, ph / s, ph % s);
-              g_ky0 = g.ky0; g_kx0 = g.kx0; g_nky = g.nky; g_nkx = g.nkx; base_y = g.oy_off - p.oy_min; base_x = g.ox_off - p.ox_min;
-            }
-            const uint32_t tmem_ph = tmem_d + (uint32_t)ph * 32u;
-            uint32_t acc_ph = kAll ? (uint32_t)(ch != 0) : acc;
-            for (int i = 0; i < g_nky; ++i) {
-              const int dy = (p.mode == 0) ? i : base_y + g_nky - 1 - i;
-              for (int j = 0; j < g_nkx; ++j) {
-                const int dx = (p.mode == 0) ? j : base_x + g_nkx - 1 - j;
-                const uint64_t ad = a_desc0 + (uint64_t)(((uint32_t)(dy * p.halo_w + dx) * row_b) >> 4);
-                const uint32_t w_idx = kAll ? (uint32_t)(((g_ky0 + i * s) * p.kw + (g_kx0 + j * s)) * p.chunks + ch)
-                                            : (uint32_t)((i * g_nkx + j) * p.chunks + ch);
-                const uint64_t bd = b_desc0 + (uint64_t)((w_idx * p.b_tap_bytes) >> 4);
+          {
+            const uint32_t ch_off = ((uint32_t)ch * p.b_tap_bytes) >> 4;
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              if (tp < ntaps) {
+                const uint64_t ad = a_desc0 + (uint64_t)a_tap[tp], bd = b_desc0 + (uint64_t)(b_tap[tp] + ch_off);
                 if (p.f16) {
 #pragma unroll
                   for (int kk = 0; kk < kKC / 16; ++kk) {  // UMMA K = 16 for fp16: 32 bytes along the row
-                    umma_f16(tmem_ph, ad + 2 * kk, bd + 2 * kk, idesc, acc_ph);
-                    acc_ph = 1;
+                    umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                    acc = 1;
                   }
                 } else {
 #pragma unroll
                   for (int kk = 0; kk < kKC / 8; ++kk) {   // UMMA K = 8 for TF32: 32 bytes along the swizzled row
-                    umma_tf32(tmem_ph, ad + 2 * kk, bd + 2 * kk, idesc, acc_ph);
-                    acc_ph = 1;
+                    umma_tf32(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                    acc = 1;
                   }
                 }
               }
             }
-            if (!kAll) acc = acc_ph;
           }
           umma_commit(&empty[r.st]);               // frees the stage once these MMAs have read it
         }

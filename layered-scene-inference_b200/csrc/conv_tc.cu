@@ -233,19 +233,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     if (elect_one()) {
       // ---------------- TMA producer ----------------
-      int it = 0;                                // ring position, continues across tiles
+      int st = 0; uint32_t ph = 0;               // ring position, continues across tiles (no integer division per stage:
+                                                 // this thread is one dependent instruction stream)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = tile_coord(p, tile, s);
         const int k_iters = p.xm ? c.nky * chunks : c.nky * c.nkx * chunks;
-        for (int k = 0; k < k_iters; ++k, ++it) {
-          const int st = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+        int kyi_c = 0, ch_c = 0;                 // k = kyi_c * chunks + ch_c (xm) / tap * chunks + ch_c
+        for (int k = 0; k < k_iters; ++k, st = (st + 1 == kStages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u), ch_c = (ch_c + 1 == chunks ? 0 : ch_c + 1), kyi_c += (ch_c == 0 ? 1 : 0)) {
           mbar_wait(&empty[st], ph ^ 1);
           uint8_t* sa = smem + st * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           if (p.xm) {
             // one halo tile (halo_w x th pixels) per (ky, chunk); tap j along x reads it shifted by off_j pixels
-            const int kyi = k / chunks, c0 = (k - kyi * chunks) * kKC;
+            const int kyi = kyi_c, c0 = ch_c * kKC;
             const int ky = c.ky0 + kyi * s;
             int ys, xs_min;
             if (p.mode == 0) { ys = c.y0 - p.pad_t + ky; xs_min = c.x0 - p.pad_l; }
@@ -259,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             continue;
           }
-          const int tap = k / chunks, c0 = (k - tap * chunks) * kKC;
+          const int tap = kyi_c, c0 = ch_c * kKC;
           const int ky = c.ky0 + (tap / c.nkx) * s, kx = c.kx0 + (tap % c.nkx) * s;
           int ys, xs;
           if (p.mode == 0) { ys = c.y0 * p.stride - p.pad_t + ky; xs = c.x0 * p.stride - p.pad_l + kx; }
@@ -279,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t idesc = p.h16 ? ((1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
                                    : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
       const uint32_t layout = p.h16 ? 4u : 2u, sbo_dense = p.h16 ? 512u : 1024u;
-      int it = 0, tcount = 0;
+      int st = 0, tcount = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const TileCoord c = tile_coord(p, tile, s);
         const int k_iters = p.xm ? c.nky * chunks : c.nky * c.nkx * chunks;
@@ -287,9 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty[buf], ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
-        for (int k = 0; k < k_iters; ++k, ++it) {
-          const int st = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+        for (int k = 0; k < k_iters; ++k, st = (st + 1 == kStages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           mbar_wait(&full[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           // descriptors advance by adding (byte offset >> 4) to the start-address field: every operand lives below
