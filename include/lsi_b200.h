@@ -253,11 +253,16 @@ LSI_B200_API int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* 
  * __half tensors, strides in elements as before).  Used between halo layers of one head (upcnv1 -> upcnv1b -> pred,
  * nets.py:87-114,137-159): the consumer normalises on load and feeds fp16 MMAs anyway, so storing the raw output in
  * fp16 halves the HBM bytes of these byte-bound layers.  in_f16 requires in_bn_stats; out_f16 a plain 32/64-channel
- * output (epilogue 0).  Statistics are reduced from the fp32 accumulators, before the rounding. */
-LSI_B200_API int lsi_b200_conv2d_halo_h(const lsi_b200_conv_desc* d, const void* in, int in_f16, const float* in_bn_stats,
-                                        const float* in_bn_beta, const float* w, const float* bias, const float* out_scale,
-                                        void* out, int out_f16, float* out_bn_stats, float bn_eps, void* workspace,
-                                        size_t workspace_bytes, void* stream);
+ * output (epilogue 0).  Statistics are reduced from the fp32 accumulators, before the rounding.
+ * in_b (optional): second input source = tf.concat([in, in_b], axis=3) on the fly (the U-Net skip, nets.py:108-109):
+ * channels [0, c_in_a) come from `in` (pending batch norm, in_bn_stats/in_bn_beta have c_in_a entries), channels
+ * [c_in_a, c_in) from `in_b` (pixel stride in_b_c_stride), which is already normalised; same element type as `in`. */
+LSI_B200_API int lsi_b200_conv2d_halo_h_supported(const lsi_b200_conv_desc* d);   /* with in_f16 != 0 (fp16 filter bank) */
+LSI_B200_API int lsi_b200_conv2d_halo_h(const lsi_b200_conv_desc* d, const void* in, const void* in_b, int c_in_a,
+                                        int in_b_c_stride, int in_f16, const float* in_bn_stats, const float* in_bn_beta,
+                                        const float* w, const float* bias, const float* out_scale, void* out, int out_f16,
+                                        float* out_bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
+                                        void* stream);
 
 /* slim.batch_norm(is_training=True, center=True, scale=False) + ReLU (nets.py:263-272): batch statistics over the
  * n_pixels = B*H*W rows; stats[c] = (mean, rsqrt(var + eps)) is kept for the backward (stats_given != 0: they were

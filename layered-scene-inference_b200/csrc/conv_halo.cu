@@ -50,6 +50,8 @@ struct HaloParams {
   int Hin, Win, Ho, Wo, Co, out_cs, Hp, Wp;
   int tiles_x, per_img, spatial_tiles;
   int chunks, kh, kw, stride, pad_t, pad_l, mode;
+  int chunks_a;              // 32-channel chunks that come from source A (pending batch norm); the rest from source B
+                             // (already normalised: tf.concat of the U-Net skip, nets.py:108-109), read through map_b
   int n_tile, epilogue, stages;
   int f16;                   // 1: transform warps also convert the normalised tile to fp16 in place; MMAs run kind::f16
   int in_f16;                // 1: the input tensor is stored as fp16 (RAW output of a producer run with out_f16): 64-byte rows,
@@ -282,7 +284,8 @@ __device__ __forceinline__ PhaseGeom phase_geom(const HaloParams& p, int s, int 
 //        with 8 transform warps.
 template <bool kWide, bool kAll>
 __global__ void __launch_bounds__(kAll ? kThreadsAll : (kWide ? kThreadsWide : kThreads), (kWide || kAll) ? 1 : 2)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
   // carve: [resident weights][stages x chunks x halo tile][barriers 256 B][bn scale/shift 2 x 512 B][staging 4 x 32 x 36 floats]
@@ -324,6 +327,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&xready[i], kBig ? 8 : 4); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kAll ? 256 : 128); }
     mbar_init(wfull, 1);
@@ -335,8 +339,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   if (bn_in) {   // y = max(x * a + b, 0) with a = rstd, b = beta - mean * rstd
     for (int c = threadIdx.x; c < p.chunks * kKC; c += blockDim.x) {
-      const float mean = __ldg(p.in_stats + 2 * c), rstd = __ldg(p.in_stats + 2 * c + 1);
-      bn_a[c] = rstd; bn_b[c] = fmaf(-mean, rstd, __ldg(p.in_beta + c));
+      if (c < p.chunks_a * kKC) {
+        const float mean = __ldg(p.in_stats + 2 * c), rstd = __ldg(p.in_stats + 2 * c + 1);
+        bn_a[c] = rstd; bn_b[c] = fmaf(-mean, rstd, __ldg(p.in_beta + c));
+      } else {   // source B is already normalised and >= 0: identity (the ReLU is a no-op)
+        bn_a[c] = 1.f; bn_b[c] = 0.f;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -368,7 +376,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int ch = 0; ch < p.chunks; ++ch, r.next()) {
           mbar_wait(&empty[r.st], r.ph ^ 1);
           mbar_expect_tx(&full[r.st], tx);
-          tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_a, &full[r.st], ch * kKC, x0 + ox_off, y0 + oy_off, n_img);
+          if (ch < p.chunks_a) tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_a, &full[r.st], ch * kKC, x0 + ox_off, y0 + oy_off, n_img);
+          else tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_b, &full[r.st], (ch - p.chunks_a) * kKC, x0 + ox_off, y0 + oy_off, n_img);
         }
       }
     }
@@ -774,19 +783,30 @@ extern "C" int lsi_b200_conv2d_halo_supported(const lsi_b200_conv_desc* d) {
   return halo_plan(d, &pl) ? 1 : 0;
 }
 
+// fp16-stored input (normalised on load, fp16 operands): layers whose fp16 filter bank fits although the TF32 one does not
+extern "C" int lsi_b200_conv2d_halo_h_supported(const lsi_b200_conv_desc* d) {
+  HaloPlan pl;
+  return (halo_plan(d, &pl) || halo_plan(d, &pl, true, true)) ? 1 : 0;
+}
+
 extern "C" size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc* d) {
   HaloPlan pl;
-  if (!halo_plan(d, &pl)) return 0;
+  if (!halo_plan(d, &pl) && !halo_plan(d, &pl, true, true)) return 0;
   return (size_t)d->kh * d->kw * pl.n_tile * (size_t)d->c_in * sizeof(float) + 512 + halo_stat_part_bytes(pl.n_tile);
 }
 
-static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_f16, const float* in_bn_stats, const float* in_bn_beta,
+static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const void* in_b, int c_in_a, int in_b_c_stride, int in_f16,
+                           const float* in_bn_stats, const float* in_bn_beta,
                            const float* w, const float* bias, const float* out_scale, void* out, int out_f16, float* out_bn_stats,
                            float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
   LSI_REQUIRE(d && in && w && out && workspace, "NULL pointer argument");
   HaloPlan pl;
-  LSI_REQUIRE(halo_plan(d, &pl), "shape not supported by the halo-tile tensor-core path");
+  LSI_REQUIRE(halo_plan(d, &pl) || (in_f16 && halo_plan(d, &pl, true, true)), "shape not supported by the halo-tile tensor-core path");
   LSI_REQUIRE(!in_f16 || (in_bn_stats && d->in_c_stride % 8 == 0), "fp16-stored input needs the producer's batch-norm statistics and an 8-channel-aligned pixel stride");
+  if (!in_b) c_in_a = d->c_in;
+  LSI_REQUIRE(c_in_a >= kKC && c_in_a % kKC == 0 && c_in_a <= d->c_in, "bad source split %d of %d channels", c_in_a, d->c_in);
+  LSI_REQUIRE(!in_b || (in_bn_stats && in_b_c_stride >= d->c_in - c_in_a && in_b_c_stride % (in_f16 ? 8 : 4) == 0 && ((uintptr_t)in_b & 15) == 0),
+              "second source needs pending statistics for the first one and an aligned pixel stride");
   LSI_REQUIRE(!out_f16 || (pl.n_tile == d->c_out && d->epilogue == 0), "fp16-stored output is for plain 32/64-channel conv outputs");
   LSI_REQUIRE((in_bn_stats == nullptr) == (in_bn_beta == nullptr), "in_bn_stats and in_bn_beta go together");
   // fp16 operands (same 10-bit mantissa as TF32, fp32 accumulation) whenever the transform warps rewrite the tile anyway:
@@ -820,7 +840,7 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
   p.tiles_x = (p.Wp + kTW - 1) / kTW;
   const int tiles_y = (p.Hp + kTH - 1) / kTH;
   p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
-  p.chunks = pl.chunks; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
+  p.chunks = pl.chunks; p.chunks_a = c_in_a / kKC; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
   p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0; p.in_f16 = in_f16 ? 1 : 0; p.out_f16 = out_f16 ? 1 : 0;
   p.all_phase = pl.all_phase; p.oy_min = pl.oy_min; p.ox_min = pl.ox_min;
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
@@ -840,19 +860,22 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
                                                             d->w_co_stride);
     LSI_LAUNCH_CHECK();
   }
-  CUtensorMap map_a, map_w;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)d->c_in, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
+  CUtensorMap map_a, map_b, map_w;
+  auto make_act_map = [&](CUtensorMap* m, const void* base, int channels, int cs) -> int {
+    cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
     const cuuint64_t eb = in_f16 ? 2 : 4;
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_c_stride * eb, (cuuint64_t)d->w_in * d->in_c_stride * eb,
-                             (cuuint64_t)d->h_in * d->w_in * d->in_c_stride * eb};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * eb, (cuuint64_t)d->w_in * cs * eb, (cuuint64_t)d->h_in * d->w_in * cs * eb};
     cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)pl.halo_w, (cuuint32_t)pl.halo_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&map_a, in_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(in), dims,
+    CUresult r = encode(m, in_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(base), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, in_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return LSI_B200_ECUDA; }
-  }
+    return LSI_B200_OK;
+  };
+  if (int rc = make_act_map(&map_a, in, c_in_a, d->in_c_stride)) return rc;
+  if (in_b) { if (int rc = make_act_map(&map_b, in_b, d->c_in - c_in_a, in_b_c_stride)) return rc; }
+  else map_b = map_a;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * pl.n_tile};
     cuuint64_t strides[1] = {(cuuint64_t)d->c_in * (f16 ? 2 : 4)};
@@ -883,9 +906,9 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
   }
   {
     ScopedTiming tm(kConvTc, st);
-    if (kv == 2) conv_halo_kernel<false, true><<<dim3((unsigned)n_ctas), kThreadsAll, pl.smem, st>>>(map_a, map_w, p);
-    else if (kv == 1) conv_halo_kernel<true, false><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_w, p);
-    else conv_halo_kernel<false, false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_w, p);
+    if (kv == 2) conv_halo_kernel<false, true><<<dim3((unsigned)n_ctas), kThreadsAll, pl.smem, st>>>(map_a, map_b, map_w, p);
+    else if (kv == 1) conv_halo_kernel<true, false><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_b, map_w, p);
+    else conv_halo_kernel<false, false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_b, map_w, p);
   }
   LSI_LAUNCH_CHECK();
   if (out_bn_stats) {
@@ -899,14 +922,14 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, int in_
 extern "C" int lsi_b200_conv2d_halo(const lsi_b200_conv_desc* d, const float* in, const float* in_bn_stats, const float* in_bn_beta,
                                     const float* w, const float* bias, const float* out_scale, float* out, float* out_bn_stats,
                                     float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
-  return conv2d_halo_impl(d, in, 0, in_bn_stats, in_bn_beta, w, bias, out_scale, out, 0, out_bn_stats, bn_eps, workspace,
+  return conv2d_halo_impl(d, in, nullptr, 0, 0, 0, in_bn_stats, in_bn_beta, w, bias, out_scale, out, 0, out_bn_stats, bn_eps, workspace,
                           workspace_bytes, stream);
 }
 
-extern "C" int lsi_b200_conv2d_halo_h(const lsi_b200_conv_desc* d, const void* in, int in_f16, const float* in_bn_stats,
-                                      const float* in_bn_beta, const float* w, const float* bias, const float* out_scale, void* out,
-                                      int out_f16, float* out_bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
-                                      void* stream) {
-  return conv2d_halo_impl(d, in, in_f16, in_bn_stats, in_bn_beta, w, bias, out_scale, out, out_f16, out_bn_stats, bn_eps, workspace,
-                          workspace_bytes, stream);
+extern "C" int lsi_b200_conv2d_halo_h(const lsi_b200_conv_desc* d, const void* in, const void* in_b, int c_in_a, int in_b_c_stride,
+                                      int in_f16, const float* in_bn_stats, const float* in_bn_beta, const float* w, const float* bias,
+                                      const float* out_scale, void* out, int out_f16, float* out_bn_stats, float bn_eps,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  return conv2d_halo_impl(d, in, in_b, c_in_a, in_b_c_stride, in_f16, in_bn_stats, in_bn_beta, w, bias, out_scale, out, out_f16,
+                          out_bn_stats, bn_eps, workspace, workspace_bytes, stream);
 }

@@ -234,6 +234,7 @@ def _wgrad(desc_kw, big, small, dw):
 _HALO = os.environ.get('LSI_B200_CONV_HALO', '1') != '0'
 _HALO_F16_STORE = os.environ.get('LSI_B200_HALO_F16_STORE', '1') != '0'
 _STEM_TC = os.environ.get('LSI_B200_STEM_TC', '1') != '0'
+_HALO_CONCAT = os.environ.get('LSI_B200_HALO_CONCAT', '1') != '0'
 _OUT_SCALE_CACHE = {}
 
 
@@ -280,14 +281,16 @@ def _halo_ok(d, *tensors):
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
 
 
-def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None):
-    """One halo-tile launch; x: tensor or _Pending (normalised on load)."""
+def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None, x_b=None):
+    """One halo-tile launch; x: tensor or _Pending (normalised on load); x_b: optional second source (already normalised),
+    i.e. tf.concat([x, x_b], axis=3) on the fly."""
     lib = _b200.lib()
     pend = isinstance(x, _Pending)
     xin = x.z if pend else x
     nws = int(lib.lsi_b200_conv2d_halo_workspace_bytes(d))
     ws = _tc_workspace(xin.device, nws)
-    _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), int(xin.dtype == torch.float16),
+    _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), _b200.ptr(x_b), xin.shape[3], 0 if x_b is None else x_b.shape[3],
+               int(xin.dtype == torch.float16),
                _b200.ptr(x.stats) if pend else None, _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias),
                _b200.ptr(out_scale), _b200.ptr(out), int(out.dtype == torch.float16), _b200.ptr(out_stats), BN_EPS,
                _b200.ptr(ws), ws.numel(), _b200.stream())
@@ -441,6 +444,26 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
     if not torch.is_grad_enabled() and _tc_mode():
         h = _f16_infer()
         pair = isinstance(x, (tuple, list))
+        halo_pair = None
+        if pair and h and _HALO_CONCAT and isinstance(x[0], _Pending) and x[0].z.dtype == torch.float16 and not transposed:
+            # tf.concat([pending up-conv output, skip]) -> 3x3 conv (upcnv2b): the halo kernel reads both sources, normalising
+            # the first on load, if the layer fits it (filter bank resident in shared memory)
+            pb = _dev_act(_materialize(x[1]), scope + ' input')
+            cin_t = x[0].shape[3] + pb.shape[3]
+            g2 = _Geometry(False, x[0].shape[0], x[0].shape[1], x[0].shape[2], cin_t, cout, k, stride)
+            d2 = _b200.ConvDesc(**dict(g2.fwd, in_c_stride=x[0].shape[3]))
+            if (pb.dtype == torch.float16 and _HALO and _b200.lib().lsi_b200_conv2d_halo_h_supported(d2) == 1
+                    and x[0].z.data_ptr() % 16 == 0 and pb.data_ptr() % 16 == 0):
+                halo_pair = (x[0], pb, g2, d2)
+        if halo_pair is not None:
+            pa, pb, geo, d = halo_pair
+            w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+            beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+            z = torch.empty(geo.B, geo.Ho, geo.Wo, cout, dtype=torch.float16, device=pb.device)
+            stats = torch.empty(cout, 2, dtype=torch.float32, device=pb.device)
+            _conv_halo(d, pa, w, z, out_stats=stats, x_b=pb)
+            out = _Pending(z, stats, beta)
+            return out if defer else out.materialize()
         if pair:
             a, b = (_dev_act(_materialize(t), scope + ' input') for t in x)
             ca, cin = a.shape[3], a.shape[3] + b.shape[3]

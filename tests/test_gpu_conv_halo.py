@@ -52,8 +52,9 @@ def _run(B, Hi, Wi, Cin, Cout, k, mode, bn_in, stats_out, epilogue=0, out_hw=Non
     wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
     if in_f16 or out_f16:
         xin = x.half() if in_f16 else x
-        _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), int(in_f16), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w),
-                   _b200.ptr(bias), None, _b200.ptr(out), int(out_f16), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
+        _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), None, Cin, 0, int(in_f16), _b200.ptr(in_stats), _b200.ptr(beta),
+                   _b200.ptr(w), _b200.ptr(bias), None, _b200.ptr(out), int(out_f16), _b200.ptr(st), EPS, _b200.ptr(wsb), nws,
+                   _b200.stream())
     else:
         _b200.call('lsi_b200_conv2d_halo', d, _b200.ptr(x), _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w), _b200.ptr(bias),
                    None, _b200.ptr(out), _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
@@ -121,6 +122,44 @@ def test_fp16_stored_activations(B, H, W, Cin, Cout, k, mode, in_f16, out_f16):
     mean = ref.mean(dim=(0, 1, 2)); var = ref.var(dim=(0, 1, 2), unbiased=False)
     assert rel_err(st[:, 0].cpu(), mean.cpu()) < TOL
     assert rel_err(st[:, 1].cpu(), torch.rsqrt(var + EPS).cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Ca,Cb,Cout', [(1, 16, 8, 64, 32, 64), (2, 21, 37, 64, 32, 64), (2, 32, 24, 32, 32, 32), (1, 48, 40, 64, 64, 64)])
+def test_two_source_concat_on_the_fly(B, H, W, Ca, Cb, Cout):
+    """upcnv2b's input is tf.concat([upcnv2 output (batch norm pending), skip (normalised)]): the halo kernel reads both
+    sources, normalising only the first; reference = fp32 kernel on the explicitly normalised, concatenated input."""
+    from lsi import _b200
+    from lsi.nnutils.nets import same_pad
+    lib = _b200.lib()
+    torch.manual_seed(Ca + Cb + H)
+    dev = 'cuda'
+    xa = (torch.randn(B, H, W, Ca, device=dev) * 1.7 + 0.3).half()
+    xb = torch.relu(torch.randn(B, H, W, Cb, device=dev)).half()
+    Cin = Ca + Cb
+    w = torch.randn(3, 3, Cin, Cout, device=dev) / (9 * Cin) ** 0.5
+    kw = dict(batch=B, h_in=H, w_in=W, c_in=Cin, h_out=H, w_out=W, c_out=Cout, kh=3, kw=3, stride=1, pad_top=same_pad(H, 3, 1)[0],
+              pad_left=same_pad(W, 3, 1)[0], mode=0, w_tap_stride=Cin * Cout, w_ci_stride=Cout, w_co_stride=1, out_c_stride=Cout,
+              epilogue=0, accumulate=0)
+    xaf = xa.float()
+    mean = xaf.mean(dim=(0, 1, 2)); var = xaf.var(dim=(0, 1, 2), unbiased=False)
+    in_stats = torch.stack([mean, torch.rsqrt(var + EPS)], dim=1).contiguous()
+    beta = torch.randn(Ca, device=dev) * 0.5
+    xn = torch.cat([torch.relu((xaf - mean) * in_stats[:, 1] + beta), xb.float()], dim=3).contiguous()
+    ref = torch.zeros(B, H, W, Cout, device=dev)
+    _b200.call('lsi_b200_conv2d', _b200.ConvDesc(in_c_stride=Cin, **kw), _b200.ptr(xn), _b200.ptr(w), None, _b200.ptr(ref), _b200.stream())
+    d = _b200.ConvDesc(in_c_stride=Ca, **kw)
+    assert lib.lsi_b200_conv2d_halo_h_supported(d) == 1
+    out = torch.full((B, H, W, Cout), 7.0, device=dev, dtype=torch.float16)
+    st = torch.zeros(Cout, 2, device=dev)
+    nws = lib.lsi_b200_conv2d_halo_workspace_bytes(d)
+    wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
+    _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xa), _b200.ptr(xb), Ca, Cb, 1, _b200.ptr(in_stats), _b200.ptr(beta), _b200.ptr(w),
+               None, None, _b200.ptr(out), 1, _b200.ptr(st), EPS, _b200.ptr(wsb), nws, _b200.stream())
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref.cpu()) < 3e-3
+    mean_o = ref.mean(dim=(0, 1, 2)); var_o = ref.var(dim=(0, 1, 2), unbiased=False)
+    assert rel_err(st[:, 0].cpu(), mean_o.cpu()) < TOL
+    assert rel_err(st[:, 1].cpu(), torch.rsqrt(var_o + EPS).cpu()) < TOL
 
 
 def test_fp16_stored_prediction_input():
