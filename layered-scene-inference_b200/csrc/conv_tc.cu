@@ -48,6 +48,8 @@ struct TcParams {
   int xm;                     // x-merge: 16x8 pixel tiles, ONE halo load per (ky, chunk) feeds all kx taps through shifted UMMA descriptors
   int halo_w;                 // xm: pixels per halo row (tile width 8 + taps along x - 1, or padded to 16)
   int th, tw;                 // tile height / width in pixels (8x16 default, 16x8 with xm)
+  int tn;                     // images per tile (th * tw * tn = 128): the 2x7 / 4x14 layers at the U-Net bottleneck fill a tile
+                              // with 8 / 2 whole images instead of leaving 89 % / 56 % of its rows empty
   float* stat_part;           // [gridDim.x*4][n_pad][2] per-(CTA,warp) channel sums of the output (batch-norm statistics), or NULL
   int h16;                    // 1: fp16 activations and weights (64-byte rows, 64B swizzle, kind::f16 MMAs, K = 16)
   int out_f16;                // 1: plain outputs are stored as fp16
@@ -170,12 +172,13 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile, int s) {
   TileCoord c;
   const int per_img = p.tiles_x * p.tiles_y;
-  const int spatial = per_img * p.batch;
+  const int spatial = per_img * ((p.batch + p.tn - 1) / p.tn);
   const int n_tiles_n = p.n_pad / p.n_tile;
   const int sp = tile % spatial; int rest = tile / spatial;
   const int nt = rest % n_tiles_n; const int ph = rest / n_tiles_n;
   c.n_img = sp / per_img;
   const int r = sp - c.n_img * per_img;
+  c.n_img *= p.tn;
   c.y0 = (r / p.tiles_x) * p.th; c.x0 = (r % p.tiles_x) * p.tw;
   c.n0 = nt * p.n_tile;
   c.py = (p.mode == 1) ? ph / s : 0; c.px = (p.mode == 1) ? ph % s : 0;
@@ -329,7 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     const int lg = warp & 3;                     // TMEM lane group this warp may access
     const int row = lg * 32 + lane;              // = A tile row = pixel within the patch
-    const int hy = row / p.tw, wx = row % p.tw;
+    const int hy_full = row / p.tw, wx = row % p.tw;
+    const int n_off = hy_full / p.th, hy = hy_full - n_off * p.th;   // (image within the tile, row, column)
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};   // channel (n0 + 32*i + lane) sums of this warp's pixels
     int stat_n0 = -1;
     float* stg = stat_stage + (size_t)lg * 32 * 33;
@@ -351,9 +355,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int oy = c.y0 + hy, ox = c.x0 + wx;
-      const bool in_range = oy < p.Hp && ox < p.Wp;
+      const int n_out = c.n_img + n_off;
+      const bool in_range = oy < p.Hp && ox < p.Wp && n_out < p.batch;
       if (p.mode == 1) { oy = oy * s + c.py; ox = ox * s + c.px; }
-      float* dst = p.out + ((size_t)(c.n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0;
+      float* dst = p.out + ((size_t)(n_out * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0;
       for (int cc = 0; cc < p.n_tile; cc += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc;
@@ -390,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (in_range && p.out_f16) {   // plain conv output (host guarantees epilogue 0, no accumulate, Co % 8 == 0), stored as fp16
           const int nvalid = min(min(32, p.n_tile - cc), p.Co - (c.n0 + cc));
-          __half* dh = reinterpret_cast<__half*>(p.out) + ((size_t)(c.n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0 + cc;
+          __half* dh = reinterpret_cast<__half*>(p.out) + ((size_t)(n_out * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0 + cc;
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
             if (j < nvalid)
@@ -456,6 +461,11 @@ __global__ void __launch_bounds__(256) prep_weights_f16_kernel(const float* __re
 static bool xmerge_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("LSI_B200_CONV_XMERGE"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1;
+}
+static bool batch_tiles_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("LSI_B200_CONV_BATCH_TILES"); on = (e && atoi(e) == 0) ? 0 : 1; }
   return on == 1;
 }
 static bool xmerge_tight() {
@@ -575,7 +585,14 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   // x-merge: unit-stride gathers with more than one tap along x, on images wide enough for 16x8 tiles to make sense
   const int nkx_max = (d->mode == 1) ? (d->kw + s - 1) / s : d->kw;
   p.xm = (xmerge_enabled() && (d->mode == 1 || d->stride == 1) && nkx_max >= 2 && nkx_max <= 9 && p.Hp >= 16 && p.n_pad <= 128) ? 1 : 0;
-  p.th = p.xm ? 16 : kTileH; p.tw = p.xm ? 8 : kTileW;
+  p.th = p.xm ? 16 : kTileH; p.tw = p.xm ? 8 : kTileW; p.tn = 1;
+  if (!p.xm && p.Wp <= 16 && batch_tiles_enabled()) {   // small images: whole images side by side in the 128 rows of a tile
+    const int tw = p.Wp <= 8 ? 8 : 16;
+    int th = 1;
+    while (th < p.Hp) th <<= 1;
+    if (tw * th < kTileM) { p.tw = tw; p.th = th; p.tn = kTileM / (tw * th); }
+    else if (tw == 8) { p.tw = 8; p.th = 16; }
+  }
   p.halo_w = p.xm ? (xmerge_tight() ? p.tw + nkx_max - 1 : 16) : 0;
   p.tiles_x = (p.Wp + p.tw - 1) / p.tw; p.tiles_y = (p.Hp + p.th - 1) / p.th;
   p.Ca = c_in_a; p.Cb = d->c_in - c_in_a;
@@ -609,7 +626,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
     const int es = (d->mode == 0) ? d->stride : 1;      // element (traversal) stride of the gather
     cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
     cuuint64_t strides[3] = {(cuuint64_t)cs * eb, (cuuint64_t)d->w_in * cs * eb, (cuuint64_t)d->h_in * d->w_in * cs * eb};
-    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((kTileW - 1) * es + 1), (cuuint32_t)((kTileH - 1) * es + 1), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((p.tw - 1) * es + 1), (cuuint32_t)((p.th - 1) * es + 1), (cuuint32_t)p.tn};
     if (p.xm) { box[1] = (cuuint32_t)p.halo_w; box[2] = (cuuint32_t)p.th; }
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
     CUresult r = encode(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -635,7 +652,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   const uint32_t b_bytes = ((uint32_t)p.n_tile * rb + 1023) & ~1023u;
   const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb + (uint32_t)d->kw * b_bytes : kTileM * rb + b_bytes;
   p.batch = d->batch;
-  p.total_tiles = p.tiles_x * p.tiles_y * d->batch * (p.n_pad / p.n_tile) * s * s;
+  p.total_tiles = p.tiles_x * p.tiles_y * ((d->batch + p.tn - 1) / p.tn) * (p.n_pad / p.n_tile) * s * s;
   // ring depth: 74 KB of stages (up to 4) lets 2-3 CTAs share an SM; the small-spatial layers of the trunk (fewer tiles than
   // SMs, K = 9 x 512 .. 1024) are one long TMA -> MMA latency chain per CTA, so they get the whole SM: up to 8 stages
   const bool latency_bound = p.total_tiles <= num_sms();

@@ -211,3 +211,22 @@ def test_stem_tensor_core(B, H, W, out_f16):
     mean = ref.mean(dim=(0, 1, 2)); var = ref.var(dim=(0, 1, 2), unbiased=False)
     assert rel_err(st[:, 0].cpu(), mean.cpu()) < TOL
     assert rel_err(st[:, 1].cpu(), torch.rsqrt(var + 1e-3).cpu()) < TOL
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k,s,mode', [
+    (5, 2, 7, 64, 128, 3, 1, 0),       # 2x7 images: 8 per tile, ragged batch
+    (11, 2, 7, 512, 512, 3, 1, 0),     # cnv7b
+    (3, 4, 14, 128, 64, 3, 1, 0),      # 4x14: 2 images per tile, odd batch
+    (5, 8, 28, 64, 64, 3, 2, 0),       # stride 2 down to 4x14 (element strides + batched tile)
+    (3, 4, 14, 96, 128, 3, 2, 0),      # stride 2 down to 2x7
+    (3, 2, 7, 128, 64, 4, 2, 1),       # up-conv 2x7 -> 4x14: phase space 2x7
+    (9, 1, 4, 64, 32, 4, 2, 1),
+    (4, 3, 5, 32, 32, 3, 1, 0),        # height not a power of two
+])
+def test_small_images_share_a_tile(B, H, W, Cin, Cout, k, s, mode):
+    """Images of at most 16 pixels across are batched into one 128-row tile (TMA box over several images): TF32 and fp16
+    operand modes against the fp32 kernel."""
+    out, ref = _run_both(B, H, W, Cin, Cout, k, s, mode, mode == 1)
+    assert rel_err(out.cpu(), ref.cpu()) < TOL
+    out, ref = _run_both(B, H, W, Cin, Cout, k, s, mode, mode == 1, h16=True, out_f16=True)
+    assert rel_err(out.cpu(), ref.cpu()) < 3e-3
