@@ -7,7 +7,7 @@
 // pixels (profiles/r1_splat_ablation.txt: 0.33 ms/step for loads + one coalesced reduction and no geometry at all).
 // Here every warp is persistent, owns a contiguous range of (image, row, 64-pixel segment) units and a private ring
 // of shared-memory stages that its elected lane fills with bulk asynchronous copies (cp.async.bulk -> UBLKCP, completion
-// on an mbarrier): 2-3 stages x 4 KB per warp are in flight while the warp does the geometry of the current one, so
+// on an mbarrier): 3 stages x 4 KB per warp are in flight while the warp does the geometry of the current one, so
 // the bytes in flight per SM no longer depend on occupancy x registers.  Row constants (matrix, pose class, vertical
 // weights) are recomputed only when the warp's range crosses into a new row.
 #pragma once
@@ -228,11 +228,11 @@ __device__ __forceinline__ void splat_group(const FastParams& f, const RowConst&
   }
 }
 
-// kN (1 or 2) layers of a stage x the stage's 32-lane sub-steps, as a rolled loop whose body is one splat_group:
-// two interleaved dependency chains per lane keep the register count at 80 (24 resident warps per SM), and the loop
-// body (~250 instructions) stays inside the instruction cache -- the fully unrolled stage (4 layers x 2 sub-steps,
-// ~1100 instructions) lost more to instruction-fetch stalls than it gained in ILP (profiles/r1_splat_stream_*).
-// `lane_ptr` = the lane's slot of layer u0, sub-step 0; `last` = these are the stage's last shared-memory reads.
+// kN (1, 2 or 4) layers of a stage x the stage's 32-lane sub-steps, as a rolled loop whose body is one splat_group.
+// Shipped configuration (kStreamQuad): all four layers of a group interleaved in one body (~350 instructions, 128
+// registers, 16 resident warps per SM); the two-layer variant (80 registers, 24 warps) and a fully unrolled stage
+// (~1100 instructions: instruction-fetch stalls) measured slower (profiles/r1_splat_stream_versions.txt).
+// `u0` = first layer of the group within the stage; `last` = these are the stage's last shared-memory reads.
 template <int kMode, bool kTwoRows, int kN, bool kHasMask, bool kPacked>
 __device__ __forceinline__ void pair_run(const StreamParams& p, const RowConst& rc, const unsigned char* stage, int u0,
                                          int i, int j0, int n_sub, float4* pb0, size_t acc_lstride, int lane, bool last,
