@@ -218,6 +218,44 @@ def test_f16_inference_mode_error_class():
     assert float(e_f16.max()) < 2.5 * float(e_tf32.max()) + 1e-3
 
 
+def test_f16_mode_at_bench_resolution():
+    """The bench pipeline's exact layer shapes (256x832 padded to 896, L=4; batch cut to 2): predict_ldi in the f16 mode --
+    tensor-core stem, fp16 conv_tc, all-phase upcnv1, two-source upcnv2b, fp16 halo chain, fused crop -- against the TF32
+    and fp32 modes, and the rendered view through forward_splat."""
+    from lsi.geometry import ldi
+    from lsi.nnutils import helpers, nets, train_utils
+    torch.manual_seed(3)
+    B, H, W, L = 2, 256, 832, 4
+    img = torch.rand(B, H, W, 3, device='cuda')
+    opts = train_utils.default_opts(dataset='kitti', n_layers=L, batch_size=B, img_height=H, img_width=W, zbuf_scale=50.0)
+    store = nets.ParamStore(seed=0)
+    k = torch.tensor([[721.54 * W / 1242.0, 0, 609.56 * W / 1242.0], [0, 721.54 * H / 375.0, 172.85 * H / 375.0], [0, 0, 1.0]],
+                     device='cuda').expand(B, 3, 3).contiguous()
+    rot = torch.eye(3, device='cuda').expand(B, 3, 3).contiguous()
+    t = torch.tensor([[-0.5327], [0.0], [0.0]], device='cuda').expand(B, 3, 1).contiguous()
+    pc = helpers.pixel_coords(B, H, W)
+    outs = {}
+    try:
+        for i, mode in enumerate(('fp32', 'tf32', 'f16')):
+            nets.set_conv_mode(mode)
+            with torch.no_grad():
+                pred = train_utils.predict_ldi(img, opts, store, reuse=i > 0)
+                view, _ = ldi.forward_splat(tuple(pred), pc, k, k, rot, t, compose_layers=True, bg_layer_disp=1e-3,
+                                            max_disp=0.4, zbuf_scale=50.0)
+            assert pred[0].shape == (L, B, H, W, 3) and pred[2].shape == (L, B, H, W, 1)
+            assert pred[0].dtype == torch.float32 and torch.isfinite(view).all()
+            outs[mode] = (torch.cat([pred[0], pred[2] / 0.4], dim=-1).clone(), view.clone())
+    finally:
+        nets.set_conv_mode('tf32')
+    # error class: measured against the exact fp32 mode, the f16 mode must stay within 2.5x of the TF32 mode's deviation
+    # (batch-stat BN over 28 samples per channel at the bottleneck amplifies either)
+    e = {m: ((outs[m][0] - outs['fp32'][0]).abs(), (outs[m][1] - outs['fp32'][1]).abs()) for m in ('tf32', 'f16')}
+    print('LDI  mean|d| tf32 %.3e f16 %.3e; view mean|d| tf32 %.3e f16 %.3e' % (float(e['tf32'][0].mean()), float(e['f16'][0].mean()),
+                                                                              float(e['tf32'][1].mean()), float(e['f16'][1].mean())))
+    assert float(e['f16'][0].mean()) < 2.5 * float(e['tf32'][0].mean()) + 1e-4
+    assert float(e['f16'][1].mean()) < 2.5 * float(e['tf32'][1].mean()) + 1e-4
+
+
 def test_unsupported_shapes_are_refused():
     from lsi import _b200
     lib = _b200.lib()
