@@ -2,11 +2,13 @@
 
 On the hot path these are fused into the CUDA kernels (csrc/common.cuh); the functions here exist so that
 reference call sites keep working, and are thin elementwise wrappers (API parity, not the measured path).
-`optimistic_restorer` (helpers.py:27-62) is TF-checkpoint plumbing and intentionally absent.
+`optimistic_restorer` (helpers.py:27-62) lives in lsi.nnutils.checkpoint (numpy archives keyed by the TF variable names)
+and is re-exported here under the reference's name.
 """
 import torch
 
 from lsi import _b200
+from lsi.nnutils.checkpoint import optimistic_restorer  # noqa: F401  (helpers.py:27-62)
 
 
 def transpose(rot):

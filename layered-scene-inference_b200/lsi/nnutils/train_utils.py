@@ -1,7 +1,7 @@
 """Mirror of the training wiring: lsi/nnutils/train_utils.py (Trainer: Adam, seeds, step loop) and the model/loss
 wiring of ldi_enc_dec.py (Trainer.define_pred_graph :175-228, define_loss_graph :265-410), re-hosted on torch +
-the B200 kernels.  The TF session / Supervisor / Saver / summary plumbing of the reference is out of scope; what is
-kept is the arithmetic and the hyper-parameters:
+the B200 kernels.  The TF session / Supervisor / summary plumbing of the reference is out of scope; what is kept is the
+arithmetic, the hyper-parameters and the checkpoint save / resume / pretrain-restore protocol (lsi.nnutils.checkpoint):
 
   * two U-Net towers with shared variables (src and trg image), heads, disp *= max_disp      ldi_enc_dec.py:196-221
   * view-synthesis loss                                                                      ldi_enc_dec.py:265-410
@@ -12,12 +12,14 @@ Data parallelism (not in the reference): one process per GPU, each
 batch (batch-norm statistics are per replica), then ONE all-reduce (sum) of the flat gradient buffer over NCCL and a
 fused Adam step on the flat parameter buffer with the gradients scaled by 1/world_size.
 """
+import os
 import types
 
 import torch
 
 from lsi import _b200
 from lsi.loss import loss as loss_mod
+from lsi.nnutils import checkpoint as ckpt
 from lsi.nnutils import helpers as nn_helpers
 from lsi.nnutils import nets
 
@@ -196,6 +198,56 @@ class Trainer(object):
         pc = nn_helpers.pixel_coords(b, h, w, device=batch['imgs_src'].device)
         return loss_mod.view_synthesis_loss(ldi_src, ldi_trg, batch['imgs_src'], batch['imgs_trg'], pc, batch['k_s'],
                                             batch['k_t'], batch['rot_mat'], batch['trans_mat'], self.opts)
+
+    # ---- checkpoints (train_utils.py:172-200, 224-232) -----------------------------------------------------------
+    def _adam_slots(self):
+        if self.m is None or self.store.flat is None:
+            return None, None
+        m, v, off = {}, {}, 0
+        for k in sorted(self.store.vars):
+            n = self.store.vars[k].numel()
+            m[k] = self.m[off:off + n].view(self.store.vars[k].shape)
+            v[k] = self.v[off:off + n].view(self.store.vars[k].shape)
+            off += n
+        return m, v
+
+    def save(self, checkpoint_dir, step):
+        """train_utils.py:224-232: step == 'latest' -> model.latest, else model-<global_step>.  Variables under their TF
+        names, global_step and the Adam slots."""
+        m, v = self._adam_slots()
+        return ckpt.save_checkpoint(ckpt.checkpoint_path(checkpoint_dir, step), self.store.vars, self.step_count, m, v)
+
+    def restore(self, path):
+        """saver.restore (train_utils.py:195): every variable must be present; resumes global_step and the Adam slots."""
+        r = ckpt.optimistic_restorer(path, self.store)
+        if r.new_vars or r.shape_mismatch:
+            raise RuntimeError('checkpoint %s does not match the model: missing %s, shape mismatch %s'
+                               % (path, r.new_vars[:5], r.shape_mismatch[:5]))
+        self.step_count = r.restore(self.store)
+        saved = ckpt.read_checkpoint(path)
+        m, v = self._adam_slots()
+        if m is not None:
+            with torch.no_grad():
+                for k in m:
+                    if k + '/Adam' in saved and k + '/Adam_1' in saved:
+                        m[k].copy_(torch.from_numpy(saved[k + '/Adam']).to(m[k].device))
+                        v[k].copy_(torch.from_numpy(saved[k + '/Adam_1']).to(v[k].device))
+        return self.step_count
+
+    def init_from_checkpoints(self, checkpoint_dir, pretrain_name=None, pretrain_iter=0):
+        """train_utils.py:176-200: resume from the latest checkpoint of checkpoint_dir if there is one; otherwise, with
+        pretrain_name, optimistically restore <checkpoint_dir>/../<pretrain_name>/model-<pretrain_iter> (variables that
+        exist there with the same shape; the rest keep their initialisation).  Returns what happened."""
+        latest = ckpt.latest_checkpoint(checkpoint_dir)
+        if latest is not None:
+            self.restore(latest)
+            return 'resumed', latest
+        if pretrain_name:
+            path = ckpt.checkpoint_path(os.path.normpath(os.path.join(checkpoint_dir, '..', pretrain_name)), pretrain_iter)
+            r = ckpt.optimistic_restorer(path, self.store)
+            self.step_count = r.restore(self.store)
+            return 'pretrained', path
+        return 'fresh', None
 
     def train_step(self, batch):
         """forward -> loss -> backward -> all-reduce(sum) of the flat gradients -> Adam.  Returns (total_loss, parts)."""
