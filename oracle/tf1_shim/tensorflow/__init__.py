@@ -294,6 +294,17 @@ def clip_by_value(x, lo, hi):
     return Tensor(torch.maximum(torch.minimum(t, hi_t), lo_t))
 
 
+def pad(tensor, paddings, mode='CONSTANT', constant_values=0):
+    """[TF1.4] tf.pad, CONSTANT mode: paddings [rank, 2] = (before, after) per dimension."""
+    t = _raw(tensor)
+    pads = _raw(paddings).to(torch.int64).tolist()
+    assert mode == 'CONSTANT' and len(pads) == t.dim()
+    flat = []
+    for before, after in reversed(pads):          # torch pads the last dimension first
+        flat += [int(before), int(after)]
+    return Tensor(torch.nn.functional.pad(t, flat, value=constant_values))
+
+
 def equal(a, b):
     ta = _raw(a)
     return Tensor(torch.eq(ta, _raw(b, like=ta)))
