@@ -290,6 +290,12 @@ LSI_B200_API int lsi_b200_sigmoid_backward(const float* y, const float* dy, floa
 LSI_B200_API int lsi_b200_adam_step(float* params, const float* grads, float* m, float* v, long long n, float learning_rate,
                                     float beta1, float beta2, float epsilon, long long step, float grad_scale, void* stream);
 
+/* KITTI loader data path (lsi/data/kitti/data.py:247-266): 8-bit HWC image (c_in channels, the first nc are used) -> float
+ * [h_out, w_out, nc] in [0, 1], resized with the semantics of tf.image.resize_images(method=AREA) (exact area weighting,
+ * any scale factor). */
+LSI_B200_API int lsi_b200_area_resize_u8(const unsigned char* in, int h_in, int w_in, int c_in, float* out, int h_out,
+                                         int w_out, int nc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
