@@ -218,6 +218,27 @@ LSI_B200_API int lsi_b200_conv2d_tc_h(const lsi_b200_conv_desc* d, const void* i
                                       int in_b_c_stride, const float* w, const float* bias, void* out, int out_f16,
                                       float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split-precision mode (lsi.nnutils.nets.set_conv_mode('split'); layout and error analysis in csrc/split.cuh): the reference
+ * CNN is fp32 (lsi/nnutils/nets.py:263-348) and tcgen05 has no fp32 MMA, so every activation and weight is carried as a pair of
+ * fp16 numbers (hi, lo * 2^11) -- 22 mantissa bits -- and every fp32 product becomes three exact fp16 products accumulated in
+ * fp32 TMEM.  A split tensor [pixels][channels] (channels % 32 == 0) has the byte size and pixel/chunk addresses of the fp32
+ * tensor: per pixel and 32-channel chunk 64 bytes of hi values then 64 bytes of lo values.
+ *
+ * lsi_b200_conv2d_tc_s: lsi_b200_conv2d_tc on split inputs (strides in channels, multiples of 32).  out_kind 0: fp32 output,
+ * any epilogue, optional out_scale[c_out] applied after the activation (`disps *= max_disp`, ldi_enc_dec.py:213);
+ * out_kind 2: split output (plain convs, c_out % 32 == 0).  bn_stats (optional) as in lsi_b200_conv2d_tc_bnstats.
+ * Workspace: lsi_b200_conv2d_tc_workspace_bytes. */
+LSI_B200_API int lsi_b200_conv2d_tc_s(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b,
+                                      int in_b_c_stride, const float* w, const float* bias, const float* out_scale, void* out,
+                                      int out_kind, float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
+/* x -> y between fp32 [n_pixels, channels] and split tensors (x_split / y_split != 0), optionally through
+ * y = relu((x - mean) * rstd + beta) with stats[c] = (mean, rstd) (slim.batch_norm + ReLU, nets.py:263-272; beta and stats both
+ * or neither).  y == x is allowed when both sides have the same layout.  channels % 32 == 0. */
+LSI_B200_API int lsi_b200_split_convert(const void* x, int x_split, const float* beta, const float* stats, void* y, int y_split,
+                                        long long n_pixels, int channels, void* stream);
+
 /* Tensor-core stem (nets.py:273, cnv1: 7x7 stride-2 conv, 3 -> 32 channels, fp32 NHWC input with 12-byte pixels that TMA
  * cannot address): im2col built by the threads in shared memory (fp16, 64B swizzle), kind::f16 tcgen05 MMAs, fp32
  * accumulation; out is __half (out_f16 != 0) or float; bn_stats (optional) = (mean, rsqrt(biased var + eps)) of the raw

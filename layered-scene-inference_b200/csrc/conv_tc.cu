@@ -19,6 +19,7 @@
 
 #include "capi_common.h"
 #include "common.cuh"
+#include "split.cuh"
 
 namespace lsi {
 
@@ -52,7 +53,10 @@ struct TcParams {
                               // with 8 / 2 whole images instead of leaving 89 % / 56 % of its rows empty
   float* stat_part;           // [gridDim.x*4][n_pad][2] per-(CTA,warp) channel sums of the output (batch-norm statistics), or NULL
   int h16;                    // 1: fp16 activations and weights (64-byte rows, 64B swizzle, kind::f16 MMAs, K = 16)
-  int out_f16;                // 1: plain outputs are stored as fp16
+                              // 2: split-precision fp16 pairs (split.cuh): 128-byte rows [hi 32 ch | lo 32 ch], 128B swizzle, kind::f16
+                              //    MMAs over K = 64 against the doubled filter tile (rows [Whi|0] then [Wlo|Whi]); two accumulators
+  int out_f16;                // 1: plain outputs are stored as fp16; 2: as split fp16 pairs (chunk-interleaved, same bytes as fp32)
+  const float* out_scale;     // optional per-channel factor applied after the activation (bias / sigmoid epilogues), or NULL
   int stages;                 // smem ring depth (2..4): shallower rings let 2-3 CTAs share an SM so that one CTA's
                               // prologue/epilogue overlaps another's main loop
 };
@@ -196,10 +200,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t rb = p.h16 ? 64u : 128u;        // bytes of one 32-channel operand row
-  const uint32_t b_tap_bytes = ((uint32_t)p.n_tile * rb + 1023) & ~1023u;
+  const uint32_t rb = (p.h16 == 1) ? 64u : 128u; // bytes of one 32-channel operand row
+  const bool split = p.h16 == 2;
+  const int n_mma = split ? 2 * p.n_tile : p.n_tile;   // UMMA N (split: D0 = hi*Whi in columns [0,N), D1 = cross terms in [N,2N))
+  const int cm = split ? 2 : 1;                  // fp16 elements per channel in the tensor maps of the split layout
+  const uint32_t b_tap_bytes = ((uint32_t)n_mma * rb + 1023) & ~1023u;
   const uint32_t a_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb : kTileM * rb;
-  const uint32_t b_bytes = (uint32_t)p.n_tile * rb;
+  const uint32_t b_bytes = (uint32_t)n_mma * rb;
   const uint32_t stage_bytes = p.xm ? a_bytes + (uint32_t)p.kw * b_tap_bytes : a_bytes + b_tap_bytes;   // xm: up to kw weight tiles
   const int kStages = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
@@ -214,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int chunks = (p.Ca + p.Cb) / kKC;
 
   uint32_t acc_cols = 32;                        // columns of one accumulator buffer
-  while ((int)acc_cols < p.n_tile) acc_cols <<= 1;
+  while ((int)acc_cols < n_mma) acc_cols <<= 1;
   const uint32_t tmem_cols = acc_cols * 2;
 
   if (warp == 0 && lane == 0) {
@@ -254,11 +261,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.mode == 0) { ys = c.y0 - p.pad_t + ky; xs_min = c.x0 - p.pad_l; }
             else { ys = c.y0 + (c.py + p.pad_t - ky) / s; xs_min = c.x0 + (c.px + p.pad_l - (c.kx0 + (c.nkx - 1) * s)) / s; }
             mbar_expect_tx(&full[st], a_bytes + (uint32_t)c.nkx * b_bytes);
-            if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs_min, ys, c.n_img);
-            else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs_min, ys, c.n_img);
+            if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0 * cm, xs_min, ys, c.n_img);
+            else tma_load_4d(sa, &map_b, &full[st], (c0 - p.Ca) * cm, xs_min, ys, c.n_img);
             for (int j = 0; j < c.nkx; ++j) {
               const int kx = c.kx0 + j * s;
-              tma_load_2d(sb + j * b_tap_bytes, &map_w, &full[st], c0, (ky * p.kw + kx) * p.n_pad + c.n0);
+              tma_load_2d(sb + j * b_tap_bytes, &map_w, &full[st], c0 * cm, ((ky * p.kw + kx) * p.n_pad + c.n0) * cm);
             }
             continue;
           }
@@ -268,9 +275,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (p.mode == 0) { ys = c.y0 * p.stride - p.pad_t + ky; xs = c.x0 * p.stride - p.pad_l + kx; }
           else { ys = c.y0 + (c.py + p.pad_t - ky) / s; xs = c.x0 + (c.px + p.pad_l - kx) / s; }   // exact: tap list matches the phase
           mbar_expect_tx(&full[st], a_bytes + b_bytes);
-          if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0, xs, ys, c.n_img);
-          else tma_load_4d(sa, &map_b, &full[st], c0 - p.Ca, xs, ys, c.n_img);
-          tma_load_2d(sb, &map_w, &full[st], c0, (ky * p.kw + kx) * p.n_pad + c.n0);
+          if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0 * cm, xs, ys, c.n_img);
+          else tma_load_4d(sa, &map_b, &full[st], (c0 - p.Ca) * cm, xs, ys, c.n_img);
+          tma_load_2d(sb, &map_w, &full[st], c0 * cm, ((ky * p.kw + kx) * p.n_pad + c.n0) * cm);
         }
       }
     }
@@ -279,9 +286,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // ---------------- MMA issuer ----------------
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
       // (kind::f16: A/B format F16 = 0, two K = 16 steps per 32-channel chunk)
-      const uint32_t idesc = p.h16 ? ((1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
+      const uint32_t idesc = p.h16 ? ((1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
                                    : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
-      const uint32_t layout = p.h16 ? 4u : 2u, sbo_dense = p.h16 ? 512u : 1024u;
+      const uint32_t layout = (p.h16 == 1) ? 4u : 2u, sbo_dense = (p.h16 == 1) ? 512u : 1024u;
       int st = 0, tcount = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const TileCoord c = tile_coord(p, tile, s);
@@ -301,7 +308,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < c.nkx; ++j) {
               const uint32_t off = (p.mode == 0) ? (uint32_t)j : (uint32_t)(c.nkx - 1 - j);   // pixels into the halo row
               const uint64_t ad = ad0 + (uint64_t)(off * (rb >> 4)), bd = bd0 + (uint64_t)(((uint32_t)j * b_tap_bytes) >> 4);
-              if (p.h16) {
+              if (split) {               // K = 64 fp16 per 128-byte row: [hi | lo] x ([Whi | 0] ; [Wlo | Whi])
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
+              } else if (p.h16) {
 #pragma unroll
                 for (int kk = 0; kk < kKC / 16; ++kk)
                   umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
@@ -313,7 +324,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else {
             const uint64_t ad = umma_desc_any(sa, sbo_dense, layout), bd = umma_desc_any(sb, sbo_dense, layout);
-            if (p.h16) {
+            if (split) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+            } else if (p.h16) {
 #pragma unroll
               for (int kk = 0; kk < kKC / 16; ++kk)     // UMMA K = 16 for fp16: 32 bytes along the swizzled row
                 umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
@@ -377,8 +392,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
               : "r"(taddr));
+#pragma unroll
+          for (int j = 16; j < 32; ++j) r[j] = 0u;
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (split) {   // second accumulator (cross terms, scaled by 2^11): columns [n_tile + cc, ...)
+          uint32_t r1[32];
+          const uint32_t taddr1 = taddr + (uint32_t)p.n_tile;
+          if (p.n_tile - cc >= 32) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                  "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15]), "=r"(r1[16]),
+                  "=r"(r1[17]), "=r"(r1[18]), "=r"(r1[19]), "=r"(r1[20]), "=r"(r1[21]), "=r"(r1[22]), "=r"(r1[23]), "=r"(r1[24]),
+                  "=r"(r1[25]), "=r"(r1[26]), "=r"(r1[27]), "=r"(r1[28]), "=r"(r1[29]), "=r"(r1[30]), "=r"(r1[31])
+                : "r"(taddr1));
+          } else {   // n_tile == 16
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                  "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                : "r"(taddr1));
+#pragma unroll
+            for (int j = 16; j < 32; ++j) r1[j] = 0u;
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            r[j] = __float_as_uint(fmaf(__uint_as_float(r1[j]), kSplitInvScale, __uint_as_float(r[j])));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         if (cc + 32 >= p.n_tile) {               // last read of this accumulator: hand the buffer back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty[buf]);
@@ -393,7 +437,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int rr = 0; rr < 32; ++rr) { const float v = stg[rr * 33 + lane]; a += v; b2 = fmaf(v, v, b2); }
           ssum[cc >> 5] += a; ssq[cc >> 5] += b2;
         }
-        if (in_range && p.out_f16) {   // plain conv output (host guarantees epilogue 0, no accumulate, Co % 8 == 0), stored as fp16
+        if (in_range && p.out_f16 == 2) {   // plain conv output as split fp16 pairs: this chunk's 128 bytes = [hi 32 ch | lo 32 ch]
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cc);     // byte address of (pixel, chunk) is the same as in an fp32 tensor
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_pack2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), hi[j], lo[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            d4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            d4[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        } else if (in_range && p.out_f16) {   // plain conv output (host guarantees epilogue 0, no accumulate, Co % 8 == 0), stored as fp16
           const int nvalid = min(min(32, p.n_tile - cc), p.Co - (c.n0 + cc));
           __half* dh = reinterpret_cast<__half*>(p.out) + ((size_t)(n_out * p.Ho + oy) * p.Wo + ox) * p.out_cs + c.n0 + cc;
 #pragma unroll
@@ -417,6 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float v = __uint_as_float(r[j]);
                 if (p.epilogue >= 1) v += __ldg(p.bias + c.n0 + cc + j);
                 if (p.epilogue == 2) v = 1.f / (1.f + expf(-v));
+                if (p.out_scale) v *= __ldg(p.out_scale + c.n0 + cc + j);
                 if (p.accumulate) v += dst[cc + j];
                 dst[cc + j] = v;
               }
@@ -455,6 +510,24 @@ __global__ void __launch_bounds__(256) prep_weights_f16_kernel(const float* __re
     const int co = (int)((i / cin) % n_pad);
     const int tap = (int)(i / ((long long)cin * n_pad));
     wk[i] = __float2half_rn((co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f);
+  }
+}
+
+// split mode (split.cuh): [tap][Cout tile][half][n in tile][chunk][64 fp16]; half 0 rows = [w_hi | 0], half 1 rows = [w_lo | w_hi]
+__global__ void __launch_bounds__(256) prep_weights_split_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
+                                                                 int cout, int n_pad, int n_tile, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * 2 * n_pad * 2 * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % (2 * cin));
+    const long long row = i / (2 * cin);
+    const int ci = (k >> 6) * 32 + (k & 31), part = (k >> 5) & 1;
+    const int tap = (int)(row / (2 * n_pad)), rr = (int)(row % (2 * n_pad));
+    const int nt = rr / (2 * n_tile), r2 = rr % (2 * n_tile);
+    const int half = r2 / n_tile, co = nt * n_tile + (r2 % n_tile);
+    const float v = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+    const __half hi = __float2half_rn(fminf(fmaxf(v, -kSplitMax), kSplitMax));
+    const __half lo = __float2half_rn((v - __half2float(hi)) * kSplitScale);
+    wk[i] = half == 0 ? (part == 0 ? hi : __float2half_rn(0.f)) : (part == 0 ? lo : hi);
   }
 }
 
@@ -508,7 +581,7 @@ static size_t stat_part_bytes(size_t n_pad) { return (size_t)148 * 4 * 4 * n_pad
 extern "C" size_t lsi_b200_conv2d_tc_workspace_bytes(const lsi_b200_conv_desc* d) {
   if (!d) return 0;
   const size_t n_pad = (size_t)(d->c_out + 15) / 16 * 16;
-  return (size_t)d->kh * d->kw * n_pad * (size_t)d->c_in * sizeof(float) + 512 + stat_part_bytes(n_pad);
+  return 2 * (size_t)d->kh * d->kw * n_pad * (size_t)d->c_in * sizeof(float) + 512 + stat_part_bytes(n_pad);   // x2: split-mode filter tiles
 }
 
 extern "C" int lsi_b200_conv2d_tc_supported(const lsi_b200_conv_desc* d, int c_in_a) {
@@ -545,7 +618,7 @@ __global__ void __launch_bounds__(256) finalize_stats_f32_kernel(const float* __
 
 static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
                           const float* w, const float* bias, void* out, float* bn_stats, float bn_eps, void* workspace,
-                          size_t workspace_bytes, void* stream, int h16 = 0, int out_f16 = 0);
+                          size_t workspace_bytes, void* stream, int h16 = 0, int out_f16 = 0, const float* out_scale = nullptr);
 
 extern "C" int lsi_b200_conv2d_tc(const lsi_b200_conv_desc* d, const float* in_a, int c_in_a, const float* in_b,
                                   int in_b_c_stride, const float* w, const float* bias, float* out, void* workspace,
@@ -564,11 +637,15 @@ extern "C" int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const flo
 
 static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
                           const float* w, const float* bias, void* out, float* bn_stats, float bn_eps, void* workspace,
-                          size_t workspace_bytes, void* stream, int h16, int out_f16) {
+                          size_t workspace_bytes, void* stream, int h16, int out_f16, const float* out_scale) {
   LSI_REQUIRE(d && in_a && w && out && workspace, "NULL pointer argument");
-  LSI_REQUIRE(!h16 || (d->in_c_stride % 8 == 0 && (!in_b || in_b_c_stride % 8 == 0)), "fp16 activations need 8-channel-aligned pixel strides");
-  LSI_REQUIRE(!out_f16 || (d->epilogue == 0 && d->accumulate == 0 && d->c_out % 8 == 0 && d->out_c_stride % 8 == 0),
+  LSI_REQUIRE(h16 != 1 || (d->in_c_stride % 8 == 0 && (!in_b || in_b_c_stride % 8 == 0)), "fp16 activations need 8-channel-aligned pixel strides");
+  LSI_REQUIRE(h16 != 2 || (d->in_c_stride % 32 == 0 && (!in_b || in_b_c_stride % 32 == 0)), "split activations need 32-channel-aligned pixel strides");
+  LSI_REQUIRE(out_f16 != 1 || (d->epilogue == 0 && d->accumulate == 0 && d->c_out % 8 == 0 && d->out_c_stride % 8 == 0),
               "fp16 output is for plain conv outputs with a multiple of 8 channels");
+  LSI_REQUIRE(out_f16 != 2 || (h16 == 2 && d->epilogue == 0 && d->accumulate == 0 && d->c_out % 32 == 0 && d->out_c_stride % 32 == 0),
+              "split output is for plain split-mode conv outputs with a multiple of 32 channels");
+  LSI_REQUIRE(!out_scale || d->epilogue >= 1, "out_scale goes with the bias / sigmoid epilogues");
   LSI_REQUIRE(lsi_b200_conv2d_tc_supported(d, c_in_a), "shape not supported by the tensor-core path");
   LSI_REQUIRE(c_in_a == d->c_in || (in_b && in_b_c_stride % 4 == 0 && in_b_c_stride >= d->c_in - c_in_a), "bad second source");
   LSI_REQUIRE(d->epilogue == 0 || bias, "epilogue needs a bias pointer");
@@ -579,12 +656,23 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   cudaStream_t st = as_stream(stream);
 
   TcParams p;
-  p.out = static_cast<float*>(out); p.bias = bias; p.h16 = h16 ? 1 : 0; p.out_f16 = out_f16 ? 1 : 0; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
+  p.out = static_cast<float*>(out); p.bias = bias; p.out_scale = out_scale; p.h16 = h16; p.out_f16 = out_f16; p.Ho = d->h_out; p.Wo = d->w_out; p.Co = d->c_out; p.out_cs = d->out_c_stride;
   const int s = d->mode == 1 ? d->stride : 1;
   p.Hp = d->h_out / s; p.Wp = d->w_out / s;
+  p.n_pad = (d->c_out + 15) / 16 * 16;
+  p.n_tile = p.n_pad <= 128 ? p.n_pad : 128;
+  if (p.n_pad > 128 && p.n_pad % 128 != 0) p.n_tile = 64;
+  LSI_REQUIRE(p.n_pad % p.n_tile == 0 && (p.n_tile == 16 || p.n_tile % 32 == 0), "unsupported output channel count %d", d->c_out);
+  const uint32_t rb = (h16 == 1) ? 64u : 128u;
+  const int n_mma = (h16 == 2) ? 2 * p.n_tile : p.n_tile;
+  const uint32_t b_bytes = ((uint32_t)n_mma * rb + 1023) & ~1023u;
   // x-merge: unit-stride gathers with more than one tap along x, on images wide enough for 16x8 tiles to make sense
   const int nkx_max = (d->mode == 1) ? (d->kw + s - 1) / s : d->kw;
   p.xm = (xmerge_enabled() && (d->mode == 1 || d->stride == 1) && nkx_max >= 2 && nkx_max <= 9 && p.Hp >= 16 && p.n_pad <= 128) ? 1 : 0;
+  if (p.xm) {   // at least two ring stages of (halo tile + one filter tile per tap along x) must fit
+    const uint32_t hw = xmerge_tight() ? 8 + nkx_max - 1 : 16;
+    if (2 * (hw * 16 * rb + (uint32_t)d->kw * b_bytes) > 200u * 1024u) p.xm = 0;
+  }
   p.th = p.xm ? 16 : kTileH; p.tw = p.xm ? 8 : kTileW; p.tn = 1;
   if (!p.xm && p.Wp <= 16 && batch_tiles_enabled()) {   // small images: whole images side by side in the 128 rows of a tile
     const int tw = p.Wp <= 8 ? 8 : 16;
@@ -597,10 +685,6 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   p.tiles_x = (p.Wp + p.tw - 1) / p.tw; p.tiles_y = (p.Hp + p.th - 1) / p.th;
   p.Ca = c_in_a; p.Cb = d->c_in - c_in_a;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
-  p.n_pad = (d->c_out + 15) / 16 * 16;
-  p.n_tile = p.n_pad <= 128 ? p.n_pad : 128;
-  if (p.n_pad > 128 && p.n_pad % 128 != 0) p.n_tile = 64;
-  LSI_REQUIRE(p.n_pad % p.n_tile == 0 && (p.n_tile == 16 || p.n_tile % 32 == 0), "unsupported output channel count %d", d->c_out);
   p.epilogue = d->epilogue; p.accumulate = d->accumulate;
 
   // weights -> K-major [tap][n_pad][cin]
@@ -609,7 +693,10 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   {
     const long long total = (long long)taps * p.n_pad * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    if (h16)
+    if (h16 == 2)
+      prep_weights_split_kernel<<<(unsigned)(g * 4 > 148 * 8 ? 148 * 8 : g * 4), 256, 0, st>>>(
+          w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, p.n_pad, p.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
+    else if (h16)
       prep_weights_f16_kernel<<<(unsigned)g, 256, 0, st>>>(w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, p.n_pad,
                                                            d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
     else
@@ -620,13 +707,14 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
 
   // tensor maps
   const cuuint64_t eb = h16 ? 2 : 4;
+  const cuuint64_t cm = (h16 == 2) ? 2 : 1;    // split: 2 fp16 elements per channel, 64-element (128-byte) box rows = [hi | lo]
   const CUtensorMapDataType dt = h16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
-  const CUtensorMapSwizzle sw = h16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw = (h16 == 1) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   auto make_act_map = [&](CUtensorMap* m, const void* base, int channels, int cs) -> int {
     const int es = (d->mode == 0) ? d->stride : 1;      // element (traversal) stride of the gather
-    cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
-    cuuint64_t strides[3] = {(cuuint64_t)cs * eb, (cuuint64_t)d->w_in * cs * eb, (cuuint64_t)d->h_in * d->w_in * cs * eb};
-    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)((p.tw - 1) * es + 1), (cuuint32_t)((p.th - 1) * es + 1), (cuuint32_t)p.tn};
+    cuuint64_t dims[4] = {(cuuint64_t)channels * cm, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * cm * eb, (cuuint64_t)d->w_in * cs * cm * eb, (cuuint64_t)d->h_in * d->w_in * cs * cm * eb};
+    cuuint32_t box[4] = {(cuuint32_t)(kKC * cm), (cuuint32_t)((p.tw - 1) * es + 1), (cuuint32_t)((p.th - 1) * es + 1), (cuuint32_t)p.tn};
     if (p.xm) { box[1] = (cuuint32_t)p.halo_w; box[2] = (cuuint32_t)p.th; }
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
     CUresult r = encode(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -640,16 +728,14 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   if (p.Cb > 0) { if (int rc = make_act_map(&map_b, in_b, p.Cb, in_b_c_stride)) return rc; }
   else map_b = map_a;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * p.n_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * eb};
-    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)p.n_tile};
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_in * cm, (cuuint64_t)taps * p.n_pad * cm};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * cm * eb};
+    cuuint32_t box[2] = {(cuuint32_t)(kKC * cm), (cuuint32_t)n_mma};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_w, dt, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
-  const uint32_t rb = h16 ? 64u : 128u;
-  const uint32_t b_bytes = ((uint32_t)p.n_tile * rb + 1023) & ~1023u;
   const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb + (uint32_t)d->kw * b_bytes : kTileM * rb + b_bytes;
   p.batch = d->batch;
   p.total_tiles = p.tiles_x * p.tiles_y * ((d->batch + p.tn - 1) / p.tn) * (p.n_pad / p.n_tile) * s * s;
@@ -667,7 +753,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
     smem_set = smem;
   }
   int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
-  const int tmem_per_cta = 2 * (p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256);
+  const int tmem_per_cta = 2 * (n_mma <= 32 ? 32 : n_mma <= 64 ? 64 : n_mma <= 128 ? 128 : 256);
   if (ctas_per_sm > 512 / tmem_per_cta) ctas_per_sm = 512 / tmem_per_cta;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 4) ctas_per_sm = 4;
@@ -676,7 +762,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   dim3 grid((unsigned)n_ctas);
   p.stat_part = nullptr;
   if (bn_stats) {
-    p.stat_part = wk + (size_t)taps * p.n_pad * d->c_in;
+    p.stat_part = wk + (size_t)taps * p.n_pad * d->c_in * ((h16 == 2) ? 2 : 1);
     p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
     LSI_CUDA(cudaMemsetAsync(p.stat_part, 0, (size_t)n_ctas * 4 * p.n_pad * 2 * sizeof(float), st));
   }
@@ -701,4 +787,18 @@ extern "C" int lsi_b200_conv2d_tc_h(const lsi_b200_conv_desc* d, const void* in_
   LSI_REQUIRE(!bn_stats || (d && d->epilogue == 0 && d->accumulate == 0), "bn statistics need a plain conv output");
   return conv2d_tc_impl(d, in_a, c_in_a, in_b, in_b_c_stride, w, bias, out, bn_stats, bn_eps, workspace, workspace_bytes, stream, 1,
                         out_f16);
+}
+
+// Split-precision mode (csrc/split.cuh, lsi.nnutils.nets.set_conv_mode('split')): in_a / in_b are split fp16-pair tensors
+// (chunk-interleaved [hi 32 ch | lo 32 ch], same bytes as fp32; strides in channels, multiples of 32); weights are split on the fly;
+// three exact fp16 products per fp32 product accumulate in two fp32 TMEM accumulators.  out_kind 0: fp32 output (any
+// epilogue, optional out_scale per channel after the activation); 2: split output (plain convs).  bn_stats as in
+// lsi_b200_conv2d_tc_bnstats.
+extern "C" int lsi_b200_conv2d_tc_s(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
+                                    const float* w, const float* bias, const float* out_scale, void* out, int out_kind,
+                                    float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
+  LSI_REQUIRE(out_kind == 0 || out_kind == 2, "out_kind must be 0 (fp32) or 2 (split)");
+  LSI_REQUIRE(!bn_stats || (d && d->epilogue == 0 && d->accumulate == 0), "bn statistics need a plain conv output");
+  return conv2d_tc_impl(d, in_a, c_in_a, in_b, in_b_c_stride, w, bias, out, bn_stats, bn_eps, workspace, workspace_bytes, stream, 2,
+                        out_kind, out_scale);
 }

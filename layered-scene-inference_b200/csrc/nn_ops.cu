@@ -9,6 +9,7 @@
 
 #include "capi_common.h"
 #include "common.cuh"
+#include "split.cuh"
 
 namespace lsi {
 
@@ -226,6 +227,94 @@ __global__ void __launch_bounds__(256) bn_apply_h_kernel(const void* __restrict_
   }
 }
 
+
+// Split-precision activations (split.cuh): one thread per (pixel, 32-channel chunk, 8-channel group): its hi values are the
+// 16 bytes at ((pixel * C/32 + chunk) * 128 + group * 16), its lo values 64 bytes further.
+//   kIn  0: x is fp32 [P, C]      1: x is a split tensor
+//   kOut 0: y is fp32 [P, C]      1: y is a split tensor (may alias x when kIn == 1)
+//   kBn  : y = relu((x - mean) * rstd + beta) (slim.batch_norm + ReLU, nets.py:263-272), else y = x
+template <int kIn, int kOut, bool kBn>
+__global__ void __launch_bounds__(256) split_convert_kernel(const void* __restrict__ xv, const float* __restrict__ stats,
+                                                            const float* __restrict__ beta, void* __restrict__ yv, long long total8,
+                                                            unsigned c8n) {
+  // the grid stride is a multiple of c8n = C / 8, so a thread meets the same eight channels in every iteration
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((unsigned long long)i0 % c8n) * 8;
+  float sa[8], sb[8];
+  if (kBn) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float mean = __ldg(stats + 2 * (c + k)), rstd = __ldg(stats + 2 * (c + k) + 1);
+      sa[k] = rstd; sb[k] = fmaf(-mean, rstd, __ldg(beta + c + k));
+    }
+  }
+  for (long long i = i0; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    const long long s_off = (i >> 2) * 8 + (i & 3);      // uint4 index of the hi values in a split tensor (lo: + 4)
+    if (kIn == 1) {
+      const uint4 h = __ldcs(reinterpret_cast<const uint4*>(xv) + s_off), l = __ldcs(reinterpret_cast<const uint4*>(xv) + s_off + 4);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = split_unpack2(hw[k], lw[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+    } else {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(xv) + 2 * i), b = __ldcs(reinterpret_cast<const float4*>(xv) + 2 * i + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (kBn) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sa[k], sb[k]), 0.f);
+    }
+    if (kOut == 1) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_pack2(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+      reinterpret_cast<uint4*>(yv)[s_off] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      reinterpret_cast<uint4*>(yv)[s_off + 4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      reinterpret_cast<float4*>(yv)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(yv)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+}  // namespace lsi
+
+using namespace lsi;
+
+// x -> y between fp32 [n_pixels, channels] and split fp16-pair tensors (csrc/split.cuh), optionally through batch norm + ReLU
+// with given stats[c] = (mean, rstd) and beta.  x_split / y_split select the layouts; in-place (y == x) is allowed when both
+// sides have the same layout.  channels % 32 == 0.
+extern "C" int lsi_b200_split_convert(const void* x, int x_split, const float* beta, const float* stats, void* y, int y_split,
+                                      long long n_pixels, int channels, void* stream) {
+  LSI_REQUIRE(x && y, "NULL pointer argument");
+  LSI_REQUIRE((beta == nullptr) == (stats == nullptr), "beta and stats go together");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 32 && channels % 32 == 0, "channels must be a multiple of 32");
+  LSI_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "tensors must be 16-byte aligned");
+  LSI_REQUIRE(x != y || (x_split != 0) == (y_split != 0), "in-place conversion needs the same layout on both sides");
+  cudaStream_t st = as_stream(stream);
+  const long long total8 = n_pixels * channels / 8;
+  const unsigned c8n = (unsigned)channels / 8;
+  unsigned m = c8n, g256 = 256;
+  while (g256) { const unsigned t = m % g256; m = g256; g256 = t; }   // m = gcd(c8n, 256)
+  m = c8n / m;
+  unsigned grid = ew_grid(total8);
+  grid = (grid + m - 1) / m * m;
+  const int sel = (x_split ? 4 : 0) | (y_split ? 2 : 0) | (stats ? 1 : 0);
+  switch (sel) {
+    case 0: split_convert_kernel<0, 0, false><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    case 1: split_convert_kernel<0, 0, true><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    case 2: split_convert_kernel<0, 1, false><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    case 3: split_convert_kernel<0, 1, true><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    case 4: split_convert_kernel<1, 0, false><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    case 5: split_convert_kernel<1, 0, true><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    case 6: split_convert_kernel<1, 1, false><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+    default: split_convert_kernel<1, 1, true><<<grid, 256, 0, st>>>(x, stats, beta, y, total8, c8n); break;
+  }
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+namespace lsi {
 }  // namespace lsi
 
 using namespace lsi;

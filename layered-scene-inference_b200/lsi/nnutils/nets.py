@@ -148,15 +148,18 @@ def _bn_workspace(device, channels):
     return _bn_ws[key]
 
 
-_CONV_MODE = os.environ.get('LSI_B200_CONV_MODE', 'tf32')   # 'tf32' | 'fp32' | 'f16' (see set_conv_mode)
+_CONV_MODE = os.environ.get('LSI_B200_CONV_MODE', 'tf32')   # 'tf32' | 'fp32' | 'f16' | 'split' (see set_conv_mode)
 
 
 def set_conv_mode(mode):
     """'tf32' (default): tcgen05 tensor-core kernels (TF32 inputs, fp32 accumulation) wherever the layer shape allows,
     fp32 CUDA-core kernels elsewhere (the 3-channel stem, weight gradients).  'fp32': CUDA-core kernels everywhere --
-    the bit-for-bit-reproducible-arithmetic mode the 1e-4 parity tests of the CNN run in."""
+    the bit-for-bit-reproducible-arithmetic mode the 1e-4 parity tests of the CNN run in.  'split': the tensor-core mode
+    that meets the fp32 parity bars (inference path: every activation and weight is a pair of fp16 numbers carrying 22
+    mantissa bits, three exact fp16 MMAs per fp32 product, fp32 accumulation -- csrc/split.cuh; with autograd enabled
+    the layers run the 'fp32' kernels).  'f16': inference-only speed mode with plain fp16 activations."""
     global _CONV_MODE
-    if mode not in ('tf32', 'fp32', 'f16'):
+    if mode not in ('tf32', 'fp32', 'f16', 'split'):
         raise ValueError(mode)
     _CONV_MODE = mode
 
@@ -170,6 +173,49 @@ def _f16_infer():
     lives in HBM as fp16 (same 10-bit mantissa as a TF32 operand), the tensor-core kernels run kind::f16 MMAs with fp32
     accumulation and batch statistics come from the fp32 accumulators.  With autograd enabled it behaves like 'tf32'."""
     return _CONV_MODE == 'f16' and not torch.is_grad_enabled()
+
+
+def _split_infer():
+    """'split': no-grad inference path on split fp16-pair activations (see set_conv_mode)."""
+    return _CONV_MODE == 'split' and not torch.is_grad_enabled()
+
+
+class _SplitAct(object):
+    """An activation [B,H,W,C] (C % 32 == 0) in the split layout of csrc/split.cuh: per pixel and 32-channel chunk 32 fp16
+    `hi` values then 32 fp16 `lo` values (v = hi + lo / 2048) -- the byte size and chunk addresses of the fp32 tensor.
+    Exists only on the no-grad inference path of the 'split' conv mode; `.float()` converts back."""
+
+    def __init__(self, t, shape):
+        self.t, self.shape, self.device = t, torch.Size(shape), t.device
+
+    @staticmethod
+    def empty(B, H, W, C, device):
+        if C % 32:
+            raise RuntimeError('lsi_b200: split activations need a multiple of 32 channels, got %d' % C)
+        return _SplitAct(torch.empty(B, H, W, C // 32, 2, 32, dtype=torch.float16, device=device), (B, H, W, C))
+
+    @staticmethod
+    def pack(x):
+        x = _b200.dev_f32(x, 'activation')
+        B, H, W, C = x.shape
+        out = _SplitAct.empty(B, H, W, C, x.device)
+        _b200.call('lsi_b200_split_convert', _b200.ptr(x), 0, None, None, _b200.ptr(out.t), 1, B * H * W, C, _b200.stream())
+        return out
+
+    def float(self):
+        B, H, W, C = self.shape
+        out = torch.empty(B, H, W, C, dtype=torch.float32, device=self.device)
+        _b200.call('lsi_b200_split_convert', _b200.ptr(self.t), 1, None, None, _b200.ptr(out), 0, B * H * W, C, _b200.stream())
+        return out
+
+    def dim(self):
+        return 4
+
+
+def to_float(x):
+    """fp32 tensor of an activation returned by the inference paths ('split' / 'f16' modes hand their internal formats on)."""
+    x = _materialize(x)
+    return x.float() if isinstance(x, _SplitAct) or x.dtype != torch.float32 else x
 
 
 def _dev_act(t, name):
@@ -256,10 +302,20 @@ class _Pending(object):
         self.z, self.stats, self.beta = z, stats, beta
         self.shape = z.shape
         self.device = z.device
+        self._done = None
 
     def materialize(self):
+        if self._done is None:
+            self._done = self._apply()
+        return self._done
+
+    def _apply(self):
         z = self.z
         B, H, W, C = z.shape
+        if isinstance(z, _SplitAct):     # normalise + ReLU in place on the split pairs
+            _b200.call('lsi_b200_split_convert', _b200.ptr(z.t), 1, _b200.ptr(self.beta), _b200.ptr(self.stats), _b200.ptr(z.t), 1,
+                       B * H * W, C, _b200.stream())
+            return z
         if z.dtype == torch.float16 and _f16_infer():
             _b200.call('lsi_b200_bn_relu_apply_h', _b200.ptr(z), 1, _b200.ptr(self.beta), _b200.ptr(self.stats), _b200.ptr(z),
                        B * H * W, C, _b200.stream())
@@ -435,12 +491,47 @@ def ctypes_offset(t, n_floats):
     return ctypes.c_void_p(t.data_ptr() + 4 * n_floats)
 
 
+def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer):
+    """_conv_layer on the no-grad path of the 'split' mode: split fp16-pair activations in and out, lsi_b200_conv2d_tc_s
+    (RAW output + batch statistics from its epilogue), then the normalise + ReLU pass in place.  The 3-channel stem runs the
+    fp32 CUDA-core kernels (TMA cannot address 12-byte pixels) and is packed afterwards."""
+    pair = isinstance(x, (tuple, list))
+    srcs = [_materialize(t) for t in (x if pair else [x])]
+    if not pair and not isinstance(srcs[0], _SplitAct) and srcs[0].shape[3] % 32:
+        xin = _b200.dev_f32(srcs[0], scope + ' input')
+        B, H, W, cin = xin.shape
+        geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
+        w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+        beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+        return _SplitAct.pack(_ConvBNReLU.apply(xin, w, beta, geo))
+    srcs = [t if isinstance(t, _SplitAct) else _SplitAct.pack(t) for t in srcs]
+    a, b = srcs[0], (srcs[1] if pair else None)
+    B, H, W, ca = a.shape
+    cin = ca + (b.shape[3] if pair else 0)
+    geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
+    w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+    beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+    d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=ca))
+    lib = _b200.lib()
+    if lib.lsi_b200_conv2d_tc_supported(d, ca) != 1 or cout % 32:
+        raise RuntimeError('lsi_b200: layer %s (%d -> %d channels) is not supported by the split tensor-core path' % (scope, cin, cout))
+    z = _SplitAct.empty(B, geo.Ho, geo.Wo, cout, a.device)
+    stats = torch.empty(cout, 2, dtype=torch.float32, device=a.device)
+    ws = _tc_workspace(a.device, int(lib.lsi_b200_conv2d_tc_workspace_bytes(d)))
+    _b200.call('lsi_b200_conv2d_tc_s', d, _b200.ptr(a.t), ca, None if b is None else _b200.ptr(b.t), 0 if b is None else b.shape[3],
+               _b200.ptr(w), None, None, _b200.ptr(z.t), 2, _b200.ptr(stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+    out = _Pending(z, stats, beta)
+    return out if defer else out.materialize()
+
+
 def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer=False):
     """conv / up-conv + batch-stat BN + ReLU.  `x` may be a pair (a, b) standing for tf.concat([a, b], axis=3): under
     no_grad the tensor-core kernel reads the two sources directly; with autograd the concat is materialised.
     Inference path (no_grad, tensor-core mode): the conv writes its RAW output and reduces the batch statistics in its
     epilogue; with defer=True the normalise + ReLU pass is left to the consumer (`_Pending`), otherwise it runs in
     place.  A `_Pending` input is normalised on load when the halo-tile kernel supports the layer."""
+    if _split_infer():
+        return _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer)
     if not torch.is_grad_enabled() and _tc_mode():
         h = _f16_infer()
         pair = isinstance(x, (tuple, list))
@@ -571,7 +662,17 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
         w = store.get('%s/pred_%d/weights' % (base, l), geo.w_shape, reuse, 'weights')
         b = store.get('%s/pred_%d/biases' % (base, l), [nc], reuse, 'biases')
         dp = _b200.ConvDesc(**dict(geo.fwd, epilogue=2))
-        if _halo_ok(dp, feat_l.z if isinstance(feat_l, _Pending) else feat_l):
+        if _split_infer() and isinstance(_materialize(feat_l), _SplitAct):
+            # 'split' mode: bias + sigmoid + per-channel output factor in the epilogue of the split tensor-core conv, fp32 output
+            fm = _materialize(feat_l)
+            if packed is None and l == 0:
+                packed = torch.empty(n_layers, B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=fm.device)
+            y = packed[l] if packed is not None else torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=fm.device)
+            ws = _tc_workspace(fm.device, int(_b200.lib().lsi_b200_conv2d_tc_workspace_bytes(dp)))
+            _b200.call('lsi_b200_conv2d_tc_s', dp, _b200.ptr(fm.t), cin, None, 0, _b200.ptr(w), _b200.ptr(b), _b200.ptr(_out_scale),
+                       _b200.ptr(y), 0, None, BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+            preds.append(y)
+        elif _halo_ok(dp, feat_l.z if isinstance(feat_l, _Pending) else feat_l):
             if packed is None and l == 0:
                 packed = torch.empty(n_layers, B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
             y = packed[l] if packed is not None else torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)

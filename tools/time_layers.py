@@ -11,8 +11,10 @@ from lsi.nnutils import nets
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=64); ap.add_argument('--h', type=int, default=256); ap.add_argument('--w', type=int, default=896)
 ap.add_argument('--layers', type=int, default=4); ap.add_argument('--iters', type=int, default=3)
-ap.add_argument('--out_w', type=int, default=832)
+ap.add_argument('--out_w', type=int, default=832); ap.add_argument('--mode', default=None)
 a = ap.parse_args()
+if a.mode:
+    nets.set_conv_mode(a.mode)
 
 records = []
 orig_call = _b200.call
@@ -34,6 +36,10 @@ def timed_call(name, *args):
         P, C = args[5], args[6]
         key = 'bn_relu_apply_h P=%d C=%d' % (P, C)
         by = (6.0 if not args[1] else 4.0) * P * C
+    elif name == 'lsi_b200_split_convert':
+        P, C = args[6], args[7]
+        key = 'split_convert P=%d C=%d in_split=%d bn=%d' % (P, C, args[1], int(args[2] is not None))
+        by = 8.0 * P * C
     elif name == 'lsi_b200_bn_relu_forward':
         P, C = args[4], args[5]
         key = 'bn_relu_forward P=%d C=%d' % (P, C)
