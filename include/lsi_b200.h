@@ -233,6 +233,16 @@ LSI_B200_API int lsi_b200_conv2d_tc_s(const lsi_b200_conv_desc* d, const void* i
                                       int out_kind, float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes,
                                       void* stream);
 
+/* lsi_b200_conv2d_halo in the split-precision mode: one split input (in_c_stride % 32 == 0), producer's batch norm + ReLU applied
+ * to the (hi, lo) pairs of the halo tile in shared memory when in_bn_stats/in_bn_beta are given.  out_kind 0: fp32 output (the
+ * <= 4-channel prediction head with bias / sigmoid / out_scale, nets.py:139-155, or a plain 32/64-channel conv); 2: split output
+ * (plain 32/64-channel convs, out_c_stride % 32 == 0).  Workspace: lsi_b200_conv2d_halo_workspace_bytes. */
+LSI_B200_API int lsi_b200_conv2d_halo_s_supported(const lsi_b200_conv_desc* d);
+LSI_B200_API int lsi_b200_conv2d_halo_s(const lsi_b200_conv_desc* d, const void* in, const float* in_bn_stats,
+                                        const float* in_bn_beta, const float* w, const float* bias, const float* out_scale,
+                                        void* out, int out_kind, float* out_bn_stats, float bn_eps, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+
 /* x -> y between fp32 [n_pixels, channels] and split tensors (x_split / y_split != 0), optionally through
  * y = relu((x - mean) * rstd + beta) with stats[c] = (mean, rstd) (slim.batch_norm + ReLU, nets.py:263-272; beta and stats both
  * or neither).  y == x is allowed when both sides have the same layout.  channels % 32 == 0. */

@@ -22,6 +22,7 @@
 
 #include "capi_common.h"
 #include "common.cuh"
+#include "split.cuh"
 
 namespace lsi {
 
@@ -57,6 +58,8 @@ struct HaloParams {
   int in_f16;                // 1: the input tensor is stored as fp16 (RAW output of a producer run with out_f16): 64-byte rows,
                              //    64B swizzle, normalised in place by the transform warps (implies f16)
   int out_f16;               // 1: the RAW output is stored as fp16 (its only consumer normalises on load and feeds fp16 MMAs anyway)
+  int split;                 // 1: split fp16-pair activations and weights (split.cuh): 128-byte rows [hi 32 ch | lo 32 ch], kind::f16 MMAs over
+                             //    K = 64 against doubled filter tiles, two accumulators (columns [0,N) and [N,2N)); out_f16 == 2 stores split pairs
   int all_phase;             // 1 (kAll): one CTA computes all stride^2 output phases of an up-conv tile from ONE halo load/transform
   int oy_min, ox_min;        // kAll: halo origin relative to the tile origin (minimum over the phases)
   int halo_w, halo_h;
@@ -266,6 +269,62 @@ __device__ __forceinline__ void transform_tile_h(uint4* tile, const float* bn_a,
   }
 }
 
+// split input tile (split.cuh): halo_w * halo_h pixel rows of 128 bytes = [hi of 32 channels | lo of 32 channels], 128B-swizzled as
+// TMA wrote it: 16-byte chunk c (0..3 hi, 4..7 lo) of row p sits at position c ^ (p & 7).  thread -> (logical chunk c = 8 channels,
+// rows p0, p0 + kNT/4, ...): it owns the hi chunk at position c ^ (p & 7) and the matching lo chunk 4 positions (xor) away; the row
+// step is a multiple of 8, so positions and scale/shift are loop invariants.  The eight lanes of a quarter-warp cover rows r and r + 4
+// (opposite 64-byte halves): conflict-free 128-bit accesses.  y = max(v * a + b, 0) re-split in place.
+template <bool kInterior, int kNT>
+__device__ __forceinline__ void transform_tile_s(uint4* tile, const float* bn_a, const float* bn_b, int tid, const HaloParams& p,
+                                                 int ys0, int xs0) {
+  const int lane = tid & 31, c = lane & 3;
+  const int p0 = (tid >> 5) * 8 + ((lane >> 2) & 1) * 4 + (lane >> 3);
+  const int pos = c ^ (p0 & 7);
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; k += 4) {
+    const float4 a4 = *reinterpret_cast<const float4*>(bn_a + (c << 3) + k);
+    const float4 b4 = *reinterpret_cast<const float4*>(bn_b + (c << 3) + k);
+    a[k] = a4.x; a[k + 1] = a4.y; a[k + 2] = a4.z; a[k + 3] = a4.w;
+    b[k] = b4.x; b[k + 1] = b4.y; b[k + 2] = b4.z; b[k + 3] = b4.w;
+  }
+  const int npx = p.halo_w * p.halo_h;
+  constexpr int kRows = kNT / 4;                             // pixel rows covered per pass (a multiple of 8)
+  uint4* qh = tile + p0 * 8 + pos;                           // row p0 + kRows * k lives kRows * 8 uint4 further per k
+  uint4* ql = tile + p0 * 8 + (pos ^ 4);
+  for (int k0 = 0; p0 + kRows * k0 < npx; k0 += 2) {
+    uint4 vh[2], vl[2]; bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ok[u] = p0 + kRows * (k0 + u) < npx;
+      vh[u] = ok[u] ? qh[kRows * 8 * (k0 + u)] : make_uint4(0u, 0u, 0u, 0u);
+      vl[u] = ok[u] ? ql[kRows * 8 * (k0 + u)] : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      bool inb = ok[u];
+      if (!kInterior) {
+        const int pxl = p0 + kRows * (k0 + u);
+        const int hy = (int)(((uint32_t)pxl * p.div_halo_w) >> 16), hx = pxl - hy * p.halo_w;
+        inb = inb && (unsigned)(ys0 + hy) < (unsigned)p.Hin && (unsigned)(xs0 + hx) < (unsigned)p.Win;
+      }
+      const uint32_t hw[4] = {vh[u].x, vh[u].y, vh[u].z, vh[u].w}, lw[4] = {vl[u].x, vl[u].y, vl[u].z, vl[u].w};
+      uint32_t oh[4], ol[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = split_unpack2(hw[k], lw[k]);
+        const float y0 = inb ? fmaxf(fmaf(f.x, a[2 * k], b[2 * k]), 0.f) : 0.f;
+        const float y1 = inb ? fmaxf(fmaf(f.y, a[2 * k + 1], b[2 * k + 1]), 0.f) : 0.f;
+        split_pack2(y0, y1, oh[k], ol[k]);
+      }
+      if (ok[u]) {
+        qh[kRows * 8 * (k0 + u)] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        ql[kRows * 8 * (k0 + u)] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      }
+    }
+  }
+}
+
 // tap list and halo offset of output phase (py, px) of a stride-s gather in mode 1 (see the phase setup in the kernel)
 struct PhaseGeom { int ky0, kx0, nky, nkx, oy_off, ox_off; };
 __device__ __forceinline__ PhaseGeom phase_geom(const HaloParams& p, int s, int py, int px) {
@@ -321,7 +380,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int oy_off = kAll ? p.oy_min : ((p.mode == 0) ? -p.pad_t : (py + p.pad_t - (ky0 + (nky - 1) * s)) / s);
   const int ox_off = kAll ? p.ox_min : ((p.mode == 0) ? -p.pad_l : (px + p.pad_l - (kx0 + (nkx - 1) * s)) / s);
 
-  const uint32_t acc_cols = kAll ? 32u * (uint32_t)(s * s) : (p.n_tile <= 32 ? 32u : (p.n_tile <= 64 ? 64u : 128u));
+  const int n_mma = p.split ? 2 * p.n_tile : p.n_tile;   // UMMA N (split: D0 in columns [0, n_tile), D1 in [n_tile, 2 n_tile))
+  const int cm = p.split ? 2 : 1;                         // fp16 elements per channel in the tensor maps of the split layout
+  const uint32_t acc_cols = kAll ? 32u * (uint32_t)(s * s) : (n_mma <= 32 ? 32u : (n_mma <= 64 ? 64u : 128u));
   const uint32_t tmem_cols = acc_cols * 2;
 
   if (warp == 0 && lane == 0) {
@@ -361,12 +422,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int ch = 0; ch < p.chunks; ++ch)
             tma_load_2d(smem_u32(s_w) + (uint32_t)(t * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC, t * p.n_tile);
       } else {
-        mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)p.n_tile * (p.f16 ? 64u : 128u));
+        mbar_expect_tx(wfull, (uint32_t)(nky * nkx * p.chunks) * (uint32_t)n_mma * (p.f16 ? 64u : 128u));
         for (int i = 0; i < nky; ++i)
           for (int j = 0; j < nkx; ++j)
             for (int ch = 0; ch < p.chunks; ++ch)
-              tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
-                          ((ky0 + i * s) * p.kw + (kx0 + j * s)) * p.n_tile);
+              tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC * cm,
+                          ((ky0 + i * s) * p.kw + (kx0 + j * s)) * n_mma);
       }
       Ring r(p.stages);
       const uint32_t tx = (uint32_t)(p.halo_w * p.halo_h) * (p.in_f16 ? 64u : 128u);
@@ -376,8 +437,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int ch = 0; ch < p.chunks; ++ch, r.next()) {
           mbar_wait(&empty[r.st], r.ph ^ 1);
           mbar_expect_tx(&full[r.st], tx);
-          if (ch < p.chunks_a) tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_a, &full[r.st], ch * kKC, x0 + ox_off, y0 + oy_off, n_img);
-          else tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_b, &full[r.st], (ch - p.chunks_a) * kKC, x0 + ox_off, y0 + oy_off, n_img);
+          if (ch < p.chunks_a) tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_a, &full[r.st], ch * kKC * cm, x0 + ox_off, y0 + oy_off, n_img);
+          else tma_load_4d(smem_u32(s_a) + (uint32_t)r.st * stage_bytes, &map_b, &full[r.st], (ch - p.chunks_a) * kKC * cm, x0 + ox_off, y0 + oy_off, n_img);
         }
       }
     }
@@ -386,7 +447,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // ---------------- MMA issuer ----------------
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
       // (kind::f16: A/B format F16 = 0, two K = 16 steps per 32-channel chunk)
-      const uint32_t idesc = p.f16 ? ((1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
+      const uint32_t idesc = (p.f16 || p.split) ? ((1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
                                    : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
       // fp16-stored input: 64-byte rows with the 64B swizzle, 8-row groups halo_w rows apart; same shifted-start trick
       const uint32_t row_b = p.in_f16 ? 64u : 128u;
@@ -457,7 +518,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tp = 0; tp < 9; ++tp) {
               if (tp < ntaps) {
                 const uint64_t ad = a_desc0 + (uint64_t)a_tap[tp], bd = b_desc0 + (uint64_t)(b_tap[tp] + ch_off);
-                if (p.f16) {
+                if (p.split) {                             // K = 64 fp16 per 128-byte row: [hi | lo] x ([Whi | 0] ; [Wlo | Whi])
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
+                    acc = 1;
+                  }
+                } else if (p.f16) {
 #pragma unroll
                   for (int kk = 0; kk < kKC / 16; ++kk) {  // UMMA K = 16 for fp16: 32 bytes along the row
                     umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
@@ -499,7 +566,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool in_range = (y0 + hy) < p.Hp && (x0 + wx) < p.Wp;
       for (int ph = eset; ph < n_ph; ph += (kAll ? 2 : 1)) {   // kAll: one 32-column accumulator per output phase
       const int e_py = kAll ? ph / s : py, e_px = kAll ? ph % s : px;
-      for (int cc = 0; cc < (kWide ? 64 : p.n_tile); cc += 32) {
+      for (int cc = 0; cc < p.n_tile; cc += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)cc + (kAll ? (uint32_t)ph * 32u : 0u);
         if (p.n_tile - cc >= 32) {
@@ -520,7 +587,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j = 16; j < 32; ++j) r[j] = 0u;
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!kAll && p.split) {   // second accumulator (cross terms, scaled by 2^11): columns [n_tile + cc, ...)
+          uint32_t r1[32];
+          const uint32_t taddr1 = taddr + (uint32_t)p.n_tile;
+          if (p.n_tile - cc >= 32) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                  "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15]), "=r"(r1[16]),
+                  "=r"(r1[17]), "=r"(r1[18]), "=r"(r1[19]), "=r"(r1[20]), "=r"(r1[21]), "=r"(r1[22]), "=r"(r1[23]), "=r"(r1[24]),
+                  "=r"(r1[25]), "=r"(r1[26]), "=r"(r1[27]), "=r"(r1[28]), "=r"(r1[29]), "=r"(r1[30]), "=r"(r1[31])
+                : "r"(taddr1));
+          } else {   // n_tile == 16
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]), "=r"(r1[8]),
+                  "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                : "r"(taddr1));
+#pragma unroll
+            for (int j = 16; j < 32; ++j) r1[j] = 0u;
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            r[j] = __float_as_uint(fmaf(__uint_as_float(r1[j]), kSplitInvScale, __uint_as_float(r[j])));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         if (cc + 32 >= p.n_tile && ph + (kAll ? 2 : 1) >= n_ph) {   // this warp's last read of the accumulator: hand the buffer back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty[buf]);
@@ -572,7 +666,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (oy < p.Hp && ox < p.Wp) {
             if (p.mode == 1) { oy = oy * s + e_py; ox = ox * s + e_px; }
             const size_t e = ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4;
-            if (p.out_f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + e) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+            if (p.out_f16 == 2) {   // split pairs: this chunk's 128 bytes = [hi 32 ch | lo 32 ch] at the fp32 tensor's chunk address
+              uint2 h2, l2;
+              split_pack2(v.x, v.y, h2.x, l2.x); split_pack2(v.z, v.w, h2.y, l2.y);
+              uint8_t* cb = reinterpret_cast<uint8_t*>(p.out + (e - c4)) + c4 * 2;
+              *reinterpret_cast<uint2*>(cb) = h2;
+              *reinterpret_cast<uint2*>(cb + 64) = l2;
+            } else if (p.out_f16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + e) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
             else *reinterpret_cast<float4*>(p.out + e) = v;
           }
         }
@@ -617,7 +717,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float4* tile = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes);
         const float* ta = bn_a + ch * kKC; const float* tb = bn_b + ch * kKC;
         constexpr int kNT = kBig ? 256 : 128;
-        if (p.in_f16) {
+        if (p.split) {
+          if (interior) transform_tile_s<true, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
+          else transform_tile_s<false, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
+        } else if (p.in_f16) {
           if (interior) transform_tile_h<true, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
           else transform_tile_h<false, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
         } else if (p.f16) {
@@ -661,6 +764,23 @@ __global__ void __launch_bounds__(256) halo_prep_weights_f16_kernel(const float*
     const int co = (int)((i / cin) % n_pad);
     const int tap = (int)(i / ((long long)cin * n_pad));
     wk[i] = __float2half_rn((co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f);
+  }
+}
+
+// split mode (split.cuh): [tap][half][n][chunk][64 fp16]; half 0 rows = [w_hi | 0], half 1 rows = [w_lo | w_hi]
+__global__ void __launch_bounds__(256) halo_prep_weights_split_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
+                                                                      int cout, int n_tile, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * 2 * n_tile * 2 * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % (2 * cin));
+    const long long row = i / (2 * cin);
+    const int ci = (k >> 6) * 32 + (k & 31), part = (k >> 5) & 1;
+    const int tap = (int)(row / (2 * n_tile)), r2 = (int)(row % (2 * n_tile));
+    const int half = r2 / n_tile, co = r2 % n_tile;
+    const float v = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+    const __half hi = __float2half_rn(fminf(fmaxf(v, -kSplitMax), kSplitMax));
+    const __half lo = __float2half_rn((v - __half2float(hi)) * kSplitScale);
+    wk[i] = half == 0 ? (part == 0 ? hi : __float2half_rn(0.f)) : (part == 0 ? lo : hi);
   }
 }
 
@@ -712,7 +832,7 @@ struct HaloPlan {
   size_t smem;
 };
 
-bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool in_f16 = false, bool all_phase = false) {
+bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool in_f16 = false, bool all_phase = false, bool split = false) {
   if (!d) return false;
   pl->all_phase = 0; pl->oy_min = 0; pl->ox_min = 0;
   if (d->c_in % kKC != 0 || d->c_in > kMaxCin || d->c_in < kKC) return false;
@@ -730,6 +850,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool
   if (pl->nky_max * pl->nkx_max > 9) return false;
   pl->halo_w = kTW + pl->nkx_max - 1; pl->halo_h = kTH + pl->nky_max - 1;
   int w_taps = pl->nky_max * pl->nkx_max;
+  if (split && (all_phase || f16 || in_f16 || d->in_c_stride % 32 != 0)) return false;
   if (all_phase) {
     // one CTA computes every output phase: the halo is the union of the phases' windows, the whole filter bank is resident
     if (!(d->mode == 1 && s == 2 && f16 && !small_out && d->c_out == 32)) return false;
@@ -748,7 +869,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool
     w_taps = d->kh * d->kw;
   }
   pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * (in_f16 ? 64u : 128u) + 1023u) & ~1023u;
-  pl->b_tap_bytes = ((uint32_t)pl->n_tile * (f16 ? 64u : 128u) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows
+  pl->b_tap_bytes = ((uint32_t)pl->n_tile * (split ? 256u : (f16 ? 64u : 128u)) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows; split: 2 n_tile rows of 128 bytes
   pl->w_bytes = (uint32_t)(w_taps * pl->chunks) * pl->b_tap_bytes;
   const size_t fixed = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + (all_phase ? 8 : 4) * 32 * kStgPitch * sizeof(float);
   const size_t stage = (size_t)pl->halo_bytes;   // one 32-channel chunk of one tile's halo
@@ -791,30 +912,34 @@ extern "C" int lsi_b200_conv2d_halo_h_supported(const lsi_b200_conv_desc* d) {
 
 extern "C" size_t lsi_b200_conv2d_halo_workspace_bytes(const lsi_b200_conv_desc* d) {
   HaloPlan pl;
-  if (!halo_plan(d, &pl) && !halo_plan(d, &pl, true, true)) return 0;
-  return (size_t)d->kh * d->kw * pl.n_tile * (size_t)d->c_in * sizeof(float) + 512 + halo_stat_part_bytes(pl.n_tile);
+  if (!halo_plan(d, &pl) && !halo_plan(d, &pl, true, true) && !halo_plan(d, &pl, false, false, false, true)) return 0;
+  return 2 * (size_t)d->kh * d->kw * pl.n_tile * (size_t)d->c_in * sizeof(float) + 512 + halo_stat_part_bytes(pl.n_tile);   // x2: split filter tiles
 }
 
 static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const void* in_b, int c_in_a, int in_b_c_stride, int in_f16,
                            const float* in_bn_stats, const float* in_bn_beta,
                            const float* w, const float* bias, const float* out_scale, void* out, int out_f16, float* out_bn_stats,
-                           float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
+                           float bn_eps, void* workspace, size_t workspace_bytes, void* stream, int split = 0) {
   LSI_REQUIRE(d && in && w && out && workspace, "NULL pointer argument");
   HaloPlan pl;
-  LSI_REQUIRE(halo_plan(d, &pl) || (in_f16 && halo_plan(d, &pl, true, true)), "shape not supported by the halo-tile tensor-core path");
+  LSI_REQUIRE(split ? halo_plan(d, &pl, false, false, false, true) : (halo_plan(d, &pl) || (in_f16 && halo_plan(d, &pl, true, true))),
+              "shape not supported by the halo-tile tensor-core path");
+  LSI_REQUIRE(!split || (!in_f16 && !in_b && (out_f16 == 0 || out_f16 == 2)), "split mode: one split source, fp32 or split output");
+  LSI_REQUIRE(split || out_f16 != 2, "split output needs the split mode");
   LSI_REQUIRE(!in_f16 || (in_bn_stats && d->in_c_stride % 8 == 0), "fp16-stored input needs the producer's batch-norm statistics and an 8-channel-aligned pixel stride");
   if (!in_b) c_in_a = d->c_in;
   LSI_REQUIRE(c_in_a >= kKC && c_in_a % kKC == 0 && c_in_a <= d->c_in, "bad source split %d of %d channels", c_in_a, d->c_in);
   LSI_REQUIRE(!in_b || (in_bn_stats && in_b_c_stride >= d->c_in - c_in_a && in_b_c_stride % (in_f16 ? 8 : 4) == 0 && ((uintptr_t)in_b & 15) == 0),
               "second source needs pending statistics for the first one and an aligned pixel stride");
-  LSI_REQUIRE(!out_f16 || (pl.n_tile == d->c_out && d->epilogue == 0), "fp16-stored output is for plain 32/64-channel conv outputs");
+  LSI_REQUIRE(!out_f16 || (pl.n_tile == d->c_out && d->epilogue == 0), "fp16-stored / split output is for plain 32/64-channel conv outputs");
+  LSI_REQUIRE(out_f16 != 2 || d->out_c_stride % 32 == 0, "split output needs a 32-channel-aligned pixel stride");
   LSI_REQUIRE((in_bn_stats == nullptr) == (in_bn_beta == nullptr), "in_bn_stats and in_bn_beta go together");
   // fp16 operands (same 10-bit mantissa as TF32, fp32 accumulation) whenever the transform warps rewrite the tile anyway:
   // normalised post-ReLU activations are O(1), far inside fp16's range; halves the operand bytes the MMAs pull from
   // shared memory, the resource these layers are bound by
   static int f16_on = -1;
   if (f16_on < 0) { const char* e = getenv("LSI_B200_HALO_F16"); f16_on = (e && atoi(e) == 0) ? 0 : 1; }
-  const bool f16 = in_bn_stats != nullptr && (f16_on == 1 || in_f16);
+  const bool f16 = !split && in_bn_stats != nullptr && (f16_on == 1 || in_f16);
   if (f16) { LSI_REQUIRE(halo_plan(d, &pl, true, in_f16 != 0), "halo plan (fp16) failed"); }
   static int all_on = -1;
   if (all_on < 0) { const char* e = getenv("LSI_B200_HALO_ALLPHASE"); all_on = (e && atoi(e) == 0) ? 0 : 1; }
@@ -841,7 +966,8 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   const int tiles_y = (p.Hp + kTH - 1) / kTH;
   p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
   p.chunks = pl.chunks; p.chunks_a = c_in_a / kKC; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
-  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0; p.in_f16 = in_f16 ? 1 : 0; p.out_f16 = out_f16 ? 1 : 0;
+  p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0; p.in_f16 = in_f16 ? 1 : 0; p.out_f16 = out_f16;
+  p.split = split ? 1 : 0;
   p.all_phase = pl.all_phase; p.oy_min = pl.oy_min; p.ox_min = pl.ox_min;
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
   p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
@@ -852,7 +978,10 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   {
     const long long total = (long long)taps * pl.n_tile * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    if (f16)
+    if (split)
+      halo_prep_weights_split_kernel<<<(unsigned)(g * 4 > 148 * 8 ? 148 * 8 : g * 4), 256, 0, st>>>(
+          w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, pl.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
+    else if (f16)
       halo_prep_weights_f16_kernel<<<(unsigned)g, 256, 0, st>>>(w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, pl.n_tile,
                                                                 d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
     else
@@ -862,12 +991,13 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   }
   CUtensorMap map_a, map_b, map_w;
   auto make_act_map = [&](CUtensorMap* m, const void* base, int channels, int cs) -> int {
-    cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
-    const cuuint64_t eb = in_f16 ? 2 : 4;
+    const cuuint64_t cm = split ? 2 : 1;   // split: 2 fp16 elements per channel, 64-element (128-byte) box rows = [hi | lo]
+    cuuint64_t dims[4] = {(cuuint64_t)channels * cm, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
+    const cuuint64_t eb = in_f16 ? 2 : 4;   // bytes per channel (split: 2 x fp16)
     cuuint64_t strides[3] = {(cuuint64_t)cs * eb, (cuuint64_t)d->w_in * cs * eb, (cuuint64_t)d->h_in * d->w_in * cs * eb};
-    cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)pl.halo_w, (cuuint32_t)pl.halo_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(kKC * cm), (cuuint32_t)pl.halo_w, (cuuint32_t)pl.halo_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(m, in_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(base), dims,
+    CUresult r = encode(m, (in_f16 || split) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(base), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, in_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return LSI_B200_ECUDA; }
@@ -877,16 +1007,17 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   if (in_b) { if (int rc = make_act_map(&map_b, in_b, d->c_in - c_in_a, in_b_c_stride)) return rc; }
   else map_b = map_a;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * pl.n_tile};
+    const cuuint64_t cm = split ? 2 : 1;
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_in * cm, (cuuint64_t)taps * pl.n_tile * cm};
     cuuint64_t strides[1] = {(cuuint64_t)d->c_in * (f16 ? 2 : 4)};
-    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)pl.n_tile};
+    cuuint32_t box[2] = {(cuuint32_t)(kKC * cm), (cuuint32_t)(pl.n_tile * cm)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&map_w, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr,
+    CUresult r = encode(&map_w, (f16 || split) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
-  const bool wide = pl.n_tile > 32;
+  const bool wide = pl.n_tile > 32 || (split && pl.ctas_per_sm == 1);   // the 448-thread variant: 1 CTA/SM, 8 transform warps
   const int kv = pl.all_phase ? 2 : (wide ? 1 : 0);
   static size_t smem_set[3] = {0, 0, 0};
   if (pl.smem > smem_set[kv]) {
@@ -901,7 +1032,7 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   n_ctas = n_ctas / G * G;
   if (n_ctas < G) n_ctas = G;
   if (out_bn_stats) {
-    p.stat_part = wk + (size_t)taps * pl.n_tile * d->c_in;
+    p.stat_part = wk + (size_t)taps * pl.n_tile * d->c_in * (split ? 2 : 1);
     p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
   }
   {
@@ -932,4 +1063,21 @@ extern "C" int lsi_b200_conv2d_halo_h(const lsi_b200_conv_desc* d, const void* i
                                       void* workspace, size_t workspace_bytes, void* stream) {
   return conv2d_halo_impl(d, in, in_b, c_in_a, in_b_c_stride, in_f16, in_bn_stats, in_bn_beta, w, bias, out_scale, out, out_f16,
                           out_bn_stats, bn_eps, workspace, workspace_bytes, stream);
+}
+
+// Split-precision mode (csrc/split.cuh): lsi_b200_conv2d_halo on a split fp16-pair input (in_c_stride % 32 == 0), split on-the-fly
+// weights, three exact fp16 products per fp32 product in two TMEM accumulators.  in_bn_stats/in_bn_beta as above: the producer's
+// batch norm + ReLU is applied to the (hi, lo) pairs of the halo tile in shared memory.  out_kind 0: fp32 output (<= 4-channel
+// prediction head with bias / sigmoid / out_scale, or plain 32/64-channel); 2: split output (plain 32/64-channel convs).
+extern "C" int lsi_b200_conv2d_halo_s_supported(const lsi_b200_conv_desc* d) {
+  HaloPlan pl;
+  return halo_plan(d, &pl, false, false, false, true) ? 1 : 0;
+}
+
+extern "C" int lsi_b200_conv2d_halo_s(const lsi_b200_conv_desc* d, const void* in, const float* in_bn_stats, const float* in_bn_beta,
+                                      const float* w, const float* bias, const float* out_scale, void* out, int out_kind,
+                                      float* out_bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream) {
+  LSI_REQUIRE(out_kind == 0 || out_kind == 2, "out_kind must be 0 (fp32) or 2 (split)");
+  return conv2d_halo_impl(d, in, nullptr, 0, 0, 0, in_bn_stats, in_bn_beta, w, bias, out_scale, out, out_kind, out_bn_stats, bn_eps,
+                          workspace, workspace_bytes, stream, 1);
 }

@@ -72,6 +72,8 @@ SIGNATURES = {
     'lsi_b200_conv2d_halo_h': (_I, [_CP, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _F, _P, _SZ, _P]),
     'lsi_b200_conv2d_tc_h': (_I, [_CP, _P, _I, _P, _I, _P, _P, _P, _I, _P, _F, _P, _SZ, _P]),
     'lsi_b200_conv2d_tc_s': (_I, [_CP, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _F, _P, _SZ, _P]),
+    'lsi_b200_conv2d_halo_s_supported': (_I, [_CP]),
+    'lsi_b200_conv2d_halo_s': (_I, [_CP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _F, _P, _SZ, _P]),
     'lsi_b200_split_convert': (_I, [_P, _I, _P, _P, _P, _I, _LL, _I, _P]),
     'lsi_b200_conv2d_stem_tc_supported': (_I, [_CP]),
     'lsi_b200_conv2d_stem_tc_workspace_bytes': (_SZ, []),

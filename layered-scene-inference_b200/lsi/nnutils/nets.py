@@ -496,6 +496,27 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
     (RAW output + batch statistics from its epilogue), then the normalise + ReLU pass in place.  The 3-channel stem runs the
     fp32 CUDA-core kernels (TMA cannot address 12-byte pixels) and is packed afterwards."""
     pair = isinstance(x, (tuple, list))
+    lib = _b200.lib()
+    if not pair and (isinstance(x, _SplitAct) or (isinstance(x, _Pending) and isinstance(x.z, _SplitAct) and x._done is None)) \
+            and _HALO and cout % 32 == 0:
+        # full-resolution few-channel head layers: halo-tile kernel (resident filter bank, one TMA halo box per tile, a pending
+        # producer's batch norm + ReLU applied on load -- the normalised tensor never exists in HBM)
+        pend = isinstance(x, _Pending)
+        a = x.z if pend else x
+        B, H, W, ca = a.shape
+        geo = _Geometry(transposed, B, H, W, ca, cout, k, stride)
+        d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=ca))
+        if lib.lsi_b200_conv2d_halo_s_supported(d) == 1:
+            w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+            beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+            z = _SplitAct.empty(B, geo.Ho, geo.Wo, cout, a.device)
+            stats = torch.empty(cout, 2, dtype=torch.float32, device=a.device)
+            ws = _tc_workspace(a.device, int(lib.lsi_b200_conv2d_halo_workspace_bytes(d)))
+            _b200.call('lsi_b200_conv2d_halo_s', d, _b200.ptr(a.t), _b200.ptr(x.stats) if pend else None,
+                       _b200.ptr(x.beta) if pend else None, _b200.ptr(w), None, None, _b200.ptr(z.t), 2, _b200.ptr(stats), BN_EPS,
+                       _b200.ptr(ws), ws.numel(), _b200.stream())
+            out = _Pending(z, stats, beta)
+            return out if defer else out.materialize()
     srcs = [_materialize(t) for t in (x if pair else [x])]
     if not pair and not isinstance(srcs[0], _SplitAct) and srcs[0].shape[3] % 32:
         xin = _b200.dev_f32(srcs[0], scope + ' input')
@@ -512,7 +533,6 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
     w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
     beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
     d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=ca))
-    lib = _b200.lib()
     if lib.lsi_b200_conv2d_tc_supported(d, ca) != 1 or cout % 32:
         raise RuntimeError('lsi_b200: layer %s (%d -> %d channels) is not supported by the split tensor-core path' % (scope, cin, cout))
     z = _SplitAct.empty(B, geo.Ho, geo.Wo, cout, a.device)
@@ -662,15 +682,24 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
         w = store.get('%s/pred_%d/weights' % (base, l), geo.w_shape, reuse, 'weights')
         b = store.get('%s/pred_%d/biases' % (base, l), [nc], reuse, 'biases')
         dp = _b200.ConvDesc(**dict(geo.fwd, epilogue=2))
-        if _split_infer() and isinstance(_materialize(feat_l), _SplitAct):
+        if _split_infer() and isinstance(feat_l.z if isinstance(feat_l, _Pending) else feat_l, _SplitAct):
             # 'split' mode: bias + sigmoid + per-channel output factor in the epilogue of the split tensor-core conv, fp32 output
-            fm = _materialize(feat_l)
             if packed is None and l == 0:
-                packed = torch.empty(n_layers, B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=fm.device)
-            y = packed[l] if packed is not None else torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=fm.device)
-            ws = _tc_workspace(fm.device, int(_b200.lib().lsi_b200_conv2d_tc_workspace_bytes(dp)))
-            _b200.call('lsi_b200_conv2d_tc_s', dp, _b200.ptr(fm.t), cin, None, 0, _b200.ptr(w), _b200.ptr(b), _b200.ptr(_out_scale),
-                       _b200.ptr(y), 0, None, BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+                packed = torch.empty(n_layers, B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
+            y = packed[l] if packed is not None else torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
+            lib = _b200.lib()
+            pend = isinstance(feat_l, _Pending) and feat_l._done is None
+            if _HALO and nc <= 4 and lib.lsi_b200_conv2d_halo_s_supported(dp) == 1:
+                fa = feat_l.z if isinstance(feat_l, _Pending) else feat_l
+                ws = _tc_workspace(fa.device, int(lib.lsi_b200_conv2d_halo_workspace_bytes(dp)))
+                _b200.call('lsi_b200_conv2d_halo_s', dp, _b200.ptr(fa.t), _b200.ptr(feat_l.stats) if pend else None,
+                           _b200.ptr(feat_l.beta) if pend else None, _b200.ptr(w), _b200.ptr(b), _b200.ptr(_out_scale), _b200.ptr(y), 0,
+                           None, BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
+            else:
+                fm = _materialize(feat_l)
+                ws = _tc_workspace(fm.device, int(lib.lsi_b200_conv2d_tc_workspace_bytes(dp)))
+                _b200.call('lsi_b200_conv2d_tc_s', dp, _b200.ptr(fm.t), cin, None, 0, _b200.ptr(w), _b200.ptr(b), _b200.ptr(_out_scale),
+                           _b200.ptr(y), 0, None, BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
             preds.append(y)
         elif _halo_ok(dp, feat_l.z if isinstance(feat_l, _Pending) else feat_l):
             if packed is None and l == 0:

@@ -103,6 +103,74 @@ def test_upconv_bn_relu_layer_split(nets_split, cin, cout, H, W, B):
     assert e < 1e-4, e
 
 
+@pytest.mark.parametrize('halo', [True, False])
+def test_head_chain_split(nets_split, halo):
+    """Tail of one LDI head (nets.py:87-114, 139-155): 4x4/2 up-conv 64->32 -> 3x3 32->32 -> 3x3 32->4 + bias + sigmoid, every batch
+    norm + ReLU left pending and applied on load by the halo-tile kernel (halo=True) or in place by the generic path."""
+    from oracle import lsi_oracle_nets as N
+    torch.manual_seed(9)
+    B, H, W = 2, 24, 20
+    x = torch.relu(torch.randn(B, H, W, 64))
+    w1, b1 = torch.randn(4, 4, 32, 64) / 16.0, torch.randn(32) * 0.3
+    w2, b2 = torch.randn(3, 3, 32, 32) / 17.0, torch.randn(32) * 0.3
+    w3, b3 = torch.randn(3, 3, 32, 4) / 17.0, torch.randn(4) * 0.3
+    d = lambda t: t.double()
+    f = N.bn_relu(N.conv2d_transpose(d(x), d(w1)), d(b1))
+    f = N.bn_relu(N.conv2d(f, d(w2), 1), d(b2))
+    ref_feat = f
+    ref = torch.sigmoid(N.conv2d(f, d(w3), 1) + d(b3))[:, :2 * H - 3, :2 * W - 5] * torch.tensor([1.0, 1.0, 1.0, 0.4], dtype=torch.float64)
+    store = nets_split.ParamStore()
+    store.load_state_dict({'h/upcnv1/weights': w1, 'h/upcnv1/BatchNorm/beta': b1, 'h/upcnv1b/weights': w2, 'h/upcnv1b/BatchNorm/beta': b2})
+    old = nets_split._HALO
+    nets_split.set_halo_mode(halo)
+    try:
+        with torch.no_grad():
+            xs = nets_split._SplitAct.pack(x.cuda())
+            f1 = nets_split._conv_layer(store, 'h/upcnv1', xs, 32, 4, 2, reuse=True, transposed=True, defer=True)
+            assert isinstance(f1, nets_split._Pending)
+            f2 = nets_split._conv_layer(store, 'h/upcnv1b', f1, 32, 3, 1, reuse=True, defer=True)
+            assert (f1._done is None) == halo           # halo path: upcnv1's normalised output never existed in HBM
+            geo = nets_split._Geometry(False, B, 2 * H, 2 * W, 32, 4, 3, 1, out_hw=(2 * H - 3, 2 * W - 5))
+            dp = nets_split._b200.ConvDesc(**dict(geo.fwd, epilogue=2))
+            y = torch.empty(B, geo.Ho, geo.Wo, 4, device='cuda')
+            scale = torch.tensor([1.0, 1.0, 1.0, 0.4], device='cuda')
+            lib = nets_split._b200.lib()
+            w3g, b3g = w3.cuda(), b3.cuda()
+            if halo:
+                assert lib.lsi_b200_conv2d_halo_s_supported(dp) == 1
+                ws = nets_split._tc_workspace(y.device, int(lib.lsi_b200_conv2d_halo_workspace_bytes(dp)))
+                nets_split._b200.call('lsi_b200_conv2d_halo_s', dp, nets_split._b200.ptr(f2.z.t), nets_split._b200.ptr(f2.stats),
+                                      nets_split._b200.ptr(f2.beta), nets_split._b200.ptr(w3g), nets_split._b200.ptr(b3g),
+                                      nets_split._b200.ptr(scale), nets_split._b200.ptr(y), 0, None, 1e-3, nets_split._b200.ptr(ws),
+                                      ws.numel(), nets_split._b200.stream())
+            else:
+                fm = f2.materialize()
+                ws = nets_split._tc_workspace(y.device, int(lib.lsi_b200_conv2d_tc_workspace_bytes(dp)))
+                nets_split._b200.call('lsi_b200_conv2d_tc_s', dp, nets_split._b200.ptr(fm.t), 32, None, 0, nets_split._b200.ptr(w3g),
+                                      nets_split._b200.ptr(b3g), nets_split._b200.ptr(scale), nets_split._b200.ptr(y), 0, None, 1e-3,
+                                      nets_split._b200.ptr(ws), ws.numel(), nets_split._b200.stream())
+            feat = nets_split.to_float(f2)
+    finally:
+        nets_split.set_halo_mode(old)
+    e_f, e_y = rel_err(feat.cpu(), ref_feat), rel_err(y.cpu(), ref)
+    print('split head chain (halo=%s): features %.3g, prediction %.3g' % (halo, e_f, e_y))
+    assert e_f < 1e-4 and e_y < 1e-4
+
+
+def test_halo_split_plain_input_and_wide_output(nets_split):
+    """Halo-tile kernel on an already normalised split input (no transform warps involved) and with 64 output channels."""
+    from oracle import lsi_oracle_nets as N
+    torch.manual_seed(4)
+    x = torch.relu(torch.randn(1, 40, 24, 32))
+    w, beta = torch.randn(3, 3, 32, 64) / 17.0, torch.randn(64) * 0.3
+    ref = N.bn_relu(N.conv2d(x.double(), w.double(), 1), beta.double())
+    store = nets_split.ParamStore()
+    store.load_state_dict({'t/weights': w, 't/BatchNorm/beta': beta})
+    with torch.no_grad():
+        out = nets_split._conv_layer(store, 't', nets_split._SplitAct.pack(x.cuda()), 64, 3, 1, reuse=True)
+    assert rel_err(out.float().cpu(), ref) < 1e-4
+
+
 def _predict(nets, params, img, L, steps, max_disp, out_hw=None):
     store = nets.ParamStore()
     store.load_state_dict(params)
