@@ -200,13 +200,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t rb = (p.h16 == 1) ? 64u : 128u; // bytes of one 32-channel operand row
-  const bool split = p.h16 == 2;
+  const uint32_t rb = (p.h16 == 1) ? 64u : 128u; // bytes of one 32-channel activation row
+  const bool split = p.h16 >= 2;                 // 2: variant S (128-byte filter rows [Whi|0];[Wlo|Whi]), 3: variant L (64-byte filter rows Whi;Wlo)
+  const bool split_l = p.h16 == 3;
   const int n_mma = split ? 2 * p.n_tile : p.n_tile;   // UMMA N (split: D0 = hi*Whi in columns [0,N), D1 = cross terms in [N,2N))
-  const int cm = split ? 2 : 1;                  // fp16 elements per channel in the tensor maps of the split layout
-  const uint32_t b_tap_bytes = ((uint32_t)n_mma * rb + 1023) & ~1023u;
+  const int cm = split ? 2 : 1;                  // fp16 elements per channel in the activation tensor maps of the split layout
+  const int cmw = (p.h16 == 2) ? 2 : 1;          // ... and in the filter map (variant S only)
+  const uint32_t rbw = (p.h16 == 1 || split_l) ? 64u : 128u;   // bytes of one filter row
+  const uint32_t b_tap_bytes = ((uint32_t)n_mma * rbw + 1023) & ~1023u;
   const uint32_t a_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb : kTileM * rb;
-  const uint32_t b_bytes = (uint32_t)n_mma * rb;
+  const uint32_t b_bytes = (uint32_t)n_mma * rbw;
   const uint32_t stage_bytes = p.xm ? a_bytes + (uint32_t)p.kw * b_tap_bytes : a_bytes + b_tap_bytes;   // xm: up to kw weight tiles
   const int kStages = p.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
@@ -265,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             else tma_load_4d(sa, &map_b, &full[st], (c0 - p.Ca) * cm, xs_min, ys, c.n_img);
             for (int j = 0; j < c.nkx; ++j) {
               const int kx = c.kx0 + j * s;
-              tma_load_2d(sb + j * b_tap_bytes, &map_w, &full[st], c0 * cm, ((ky * p.kw + kx) * p.n_pad + c.n0) * cm);
+              tma_load_2d(sb + j * b_tap_bytes, &map_w, &full[st], c0 * cmw, ((ky * p.kw + kx) * p.n_pad + c.n0) * cm);
             }
             continue;
           }
@@ -277,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_expect_tx(&full[st], a_bytes + b_bytes);
           if (c0 < p.Ca) tma_load_4d(sa, &map_a, &full[st], c0 * cm, xs, ys, c.n_img);
           else tma_load_4d(sa, &map_b, &full[st], (c0 - p.Ca) * cm, xs, ys, c.n_img);
-          tma_load_2d(sb, &map_w, &full[st], c0 * cm, ((ky * p.kw + kx) * p.n_pad + c.n0) * cm);
+          tma_load_2d(sb, &map_w, &full[st], c0 * cmw, ((ky * p.kw + kx) * p.n_pad + c.n0) * cm);
         }
       }
     }
@@ -289,6 +292,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t idesc = p.h16 ? ((1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
                                    : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
       const uint32_t layout = (p.h16 == 1) ? 4u : 2u, sbo_dense = (p.h16 == 1) ? 512u : 1024u;
+      // variant L: filter tile = 2N rows of 64 bytes (64B swizzle): rows [0,N) = Whi, [N,2N) = Wlo.  Per chunk: a_hi x (Whi;Wlo) with
+      // N' = 2N into columns [0,2N), then a_lo x Whi with N' = N into columns [N,2N): 3N instead of 4N columns of MMA work, half the
+      // filter bytes.  The activation operand keeps its 128-byte rows / 128B swizzle (each descriptor carries its own layout).
+      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t layout_b = split_l ? 4u : layout, sbo_b = split_l ? 512u : sbo_dense;
       int st = 0, tcount = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const TileCoord c = tile_coord(p, tile, s);
@@ -304,11 +312,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // 256 KB, so there is no carry out of its 14 bits
           const uint32_t sa = smem_u32(smem + st * stage_bytes), sb = sa + a_bytes;
           if (p.xm) {
-            const uint64_t ad0 = umma_desc_any(sa, (uint32_t)p.halo_w * rb, layout), bd0 = umma_desc_any(sb, sbo_dense, layout);
+            const uint64_t ad0 = umma_desc_any(sa, (uint32_t)p.halo_w * rb, layout), bd0 = umma_desc_any(sb, sbo_b, layout_b);
             for (int j = 0; j < c.nkx; ++j) {
               const uint32_t off = (p.mode == 0) ? (uint32_t)j : (uint32_t)(c.nkx - 1 - j);   // pixels into the halo row
               const uint64_t ad = ad0 + (uint64_t)(off * (rb >> 4)), bd = bd0 + (uint64_t)(((uint32_t)j * b_tap_bytes) >> 4);
-              if (split) {               // K = 64 fp16 per 128-byte row: [hi | lo] x ([Whi | 0] ; [Wlo | Whi])
+              if (split_l) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+                  umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+                  umma_f16(tmem_d + (uint32_t)p.n_tile, ad + 4 + 2 * kk, bd + 2 * kk, idesc_n, 1u);
+              } else if (split) {        // K = 64 fp16 per 128-byte row: [hi | lo] x ([Whi | 0] ; [Wlo | Whi])
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                   umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | j | kk) != 0);
@@ -323,8 +338,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           } else {
-            const uint64_t ad = umma_desc_any(sa, sbo_dense, layout), bd = umma_desc_any(sb, sbo_dense, layout);
-            if (split) {
+            const uint64_t ad = umma_desc_any(sa, sbo_dense, layout), bd = umma_desc_any(sb, sbo_b, layout_b);
+            if (split_l) {
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk)
+                umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk)
+                umma_f16(tmem_d + (uint32_t)p.n_tile, ad + 4 + 2 * kk, bd + 2 * kk, idesc_n, 1u);
+            } else if (split) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
@@ -531,6 +553,28 @@ __global__ void __launch_bounds__(256) prep_weights_split_kernel(const float* __
   }
 }
 
+// split mode, variant L: [tap][Cout tile][half][n in tile][cin] fp16; half 0 rows = w_hi, half 1 rows = w_lo
+__global__ void __launch_bounds__(256) prep_weights_split_l_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
+                                                                   int cout, int n_pad, int n_tile, int w_tap, int w_ci, int w_co) {
+  const long long total = (long long)taps * 2 * n_pad * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const long long row = i / cin;
+    const int tap = (int)(row / (2 * n_pad)), rr = (int)(row % (2 * n_pad));
+    const int nt = rr / (2 * n_tile), r2 = rr % (2 * n_tile);
+    const int half = r2 / n_tile, co = nt * n_tile + (r2 % n_tile);
+    const float v = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
+    const __half hi = __float2half_rn(fminf(fmaxf(v, -kSplitMax), kSplitMax));
+    wk[i] = half == 0 ? hi : __float2half_rn((v - __half2float(hi)) * kSplitScale);
+  }
+}
+
+static bool split_variant_l() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("LSI_B200_SPLIT_VARIANT"); on = (e && (e[0] == 'S' || e[0] == 's')) ? 0 : 1; }
+  return on == 1;
+}
+
 static bool xmerge_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("LSI_B200_CONV_XMERGE"); on = (e && atoi(e) == 0) ? 0 : 1; }
@@ -639,11 +683,12 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
                           const float* w, const float* bias, void* out, float* bn_stats, float bn_eps, void* workspace,
                           size_t workspace_bytes, void* stream, int h16, int out_f16, const float* out_scale) {
   LSI_REQUIRE(d && in_a && w && out && workspace, "NULL pointer argument");
+  if (h16 == 2 && split_variant_l()) h16 = 3;
   LSI_REQUIRE(h16 != 1 || (d->in_c_stride % 8 == 0 && (!in_b || in_b_c_stride % 8 == 0)), "fp16 activations need 8-channel-aligned pixel strides");
-  LSI_REQUIRE(h16 != 2 || (d->in_c_stride % 32 == 0 && (!in_b || in_b_c_stride % 32 == 0)), "split activations need 32-channel-aligned pixel strides");
+  LSI_REQUIRE(h16 < 2 || (d->in_c_stride % 32 == 0 && (!in_b || in_b_c_stride % 32 == 0)), "split activations need 32-channel-aligned pixel strides");
   LSI_REQUIRE(out_f16 != 1 || (d->epilogue == 0 && d->accumulate == 0 && d->c_out % 8 == 0 && d->out_c_stride % 8 == 0),
               "fp16 output is for plain conv outputs with a multiple of 8 channels");
-  LSI_REQUIRE(out_f16 != 2 || (h16 == 2 && d->epilogue == 0 && d->accumulate == 0 && d->c_out % 32 == 0 && d->out_c_stride % 32 == 0),
+  LSI_REQUIRE(out_f16 != 2 || (h16 >= 2 && d->epilogue == 0 && d->accumulate == 0 && d->c_out % 32 == 0 && d->out_c_stride % 32 == 0),
               "split output is for plain split-mode conv outputs with a multiple of 32 channels");
   LSI_REQUIRE(!out_scale || d->epilogue >= 1, "out_scale goes with the bias / sigmoid epilogues");
   LSI_REQUIRE(lsi_b200_conv2d_tc_supported(d, c_in_a), "shape not supported by the tensor-core path");
@@ -664,8 +709,9 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   if (p.n_pad > 128 && p.n_pad % 128 != 0) p.n_tile = 64;
   LSI_REQUIRE(p.n_pad % p.n_tile == 0 && (p.n_tile == 16 || p.n_tile % 32 == 0), "unsupported output channel count %d", d->c_out);
   const uint32_t rb = (h16 == 1) ? 64u : 128u;
-  const int n_mma = (h16 == 2) ? 2 * p.n_tile : p.n_tile;
-  const uint32_t b_bytes = ((uint32_t)n_mma * rb + 1023) & ~1023u;
+  const uint32_t rbw = (h16 == 1 || h16 == 3) ? 64u : 128u;
+  const int n_mma = (h16 >= 2) ? 2 * p.n_tile : p.n_tile;
+  const uint32_t b_bytes = ((uint32_t)n_mma * rbw + 1023) & ~1023u;
   // x-merge: unit-stride gathers with more than one tap along x, on images wide enough for 16x8 tiles to make sense
   const int nkx_max = (d->mode == 1) ? (d->kw + s - 1) / s : d->kw;
   p.xm = (xmerge_enabled() && (d->mode == 1 || d->stride == 1) && nkx_max >= 2 && nkx_max <= 9 && p.Hp >= 16 && p.n_pad <= 128) ? 1 : 0;
@@ -693,7 +739,10 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   {
     const long long total = (long long)taps * p.n_pad * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    if (h16 == 2)
+    if (h16 == 3)
+      prep_weights_split_l_kernel<<<(unsigned)(g * 2 > 148 * 8 ? 148 * 8 : g * 2), 256, 0, st>>>(
+          w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, p.n_pad, p.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
+    else if (h16 == 2)
       prep_weights_split_kernel<<<(unsigned)(g * 4 > 148 * 8 ? 148 * 8 : g * 4), 256, 0, st>>>(
           w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, p.n_pad, p.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
     else if (h16)
@@ -707,7 +756,8 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
 
   // tensor maps
   const cuuint64_t eb = h16 ? 2 : 4;
-  const cuuint64_t cm = (h16 == 2) ? 2 : 1;    // split: 2 fp16 elements per channel, 64-element (128-byte) box rows = [hi | lo]
+  const cuuint64_t cm = (h16 >= 2) ? 2 : 1;    // split: 2 fp16 elements per channel, 64-element (128-byte) box rows = [hi | lo]
+  const cuuint64_t cmw = (h16 == 2) ? 2 : 1;   // filter map: variant S rows are [Whi|0] / [Wlo|Whi] (64 elements per chunk), variant L 32
   const CUtensorMapDataType dt = h16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   const CUtensorMapSwizzle sw = (h16 == 1) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   auto make_act_map = [&](CUtensorMap* m, const void* base, int channels, int cs) -> int {
@@ -728,12 +778,12 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   if (p.Cb > 0) { if (int rc = make_act_map(&map_b, in_b, p.Cb, in_b_c_stride)) return rc; }
   else map_b = map_a;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->c_in * cm, (cuuint64_t)taps * p.n_pad * cm};
-    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * cm * eb};
-    cuuint32_t box[2] = {(cuuint32_t)(kKC * cm), (cuuint32_t)n_mma};
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_in * cmw, (cuuint64_t)taps * p.n_pad * cm};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * cmw * eb};
+    cuuint32_t box[2] = {(cuuint32_t)(kKC * cmw), (cuuint32_t)n_mma};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_w, dt, 2, wk, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        (h16 == 3) ? CU_TENSOR_MAP_SWIZZLE_64B : sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
   const uint32_t stage_bytes = p.xm ? (uint32_t)p.halo_w * p.th * rb + (uint32_t)d->kw * b_bytes : kTileM * rb + b_bytes;
@@ -762,7 +812,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   dim3 grid((unsigned)n_ctas);
   p.stat_part = nullptr;
   if (bn_stats) {
-    p.stat_part = wk + (size_t)taps * p.n_pad * d->c_in * ((h16 == 2) ? 2 : 1);
+    p.stat_part = wk + (size_t)taps * p.n_pad * d->c_in * ((h16 == 2) ? 2 : 1);   // (variant L: the fp16 pair rows take the fp32 size)
     p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
     LSI_CUDA(cudaMemsetAsync(p.stat_part, 0, (size_t)n_ctas * 4 * p.n_pad * 2 * sizeof(float), st));
   }
