@@ -3,7 +3,9 @@ lsi/nnutils/helpers.py:27-62 (reference tree) re-hosted on numpy archives.
 
 A checkpoint is one `.npz` file whose keys are the reference's TF variable names (`encoder_decoder_unet/cnv1/weights`,
 `ldi_tex_disp/pixelwise_pred/upsample_0/decoder/upcnv3/BatchNorm/beta`, ...) plus `global_step`, and -- for exact resume --
-the Adam slots under TF's slot names (`<var>/Adam`, `<var>/Adam_1`).  `tools/tf1_ckpt_to_npz.py` writes the same layout
+the Adam slots under TF's slot names (`<var>/Adam`, `<var>/Adam_1`) with Adam's own step count `adam_t` (the reference's
+Saver keeps model variables and the step counter only, so its Adam restarts after every restore; a file without slots does the
+same here).  `tools/tf1_ckpt_to_npz.py` writes the same layout
 from a TF-1 `model-<step>` checkpoint where TensorFlow is installed (it is not in this image), so reference snapshots load
 through the same path.  File naming follows `Trainer.save` (train_utils.py:224-232): `model-<global_step>.npz` and
 `model.latest.npz`; the text file `checkpoint` in the directory records the most recent one, as tf.train.Saver does for
@@ -16,6 +18,17 @@ import torch
 
 INDEX_FILE = 'checkpoint'
 MODEL_NAME = 'model'
+# keys of an archive that are not model variables.  The reference creates its step counter inside tf.name_scope('train_op')
+# (train_utils.py:107-116), so a converted TF-1 snapshot carries it as 'train_op/global_step'.
+GLOBAL_STEP_KEYS = ('global_step', 'train_op/global_step')
+NON_VARIABLE_KEYS = GLOBAL_STEP_KEYS + ('adam_t',)
+
+
+def global_step_key(saved):
+    for k in GLOBAL_STEP_KEYS:
+        if k in saved:
+            return k
+    return None
 
 
 def checkpoint_path(checkpoint_dir, step):
@@ -25,10 +38,12 @@ def checkpoint_path(checkpoint_dir, step):
     return os.path.join(checkpoint_dir, '%s-%d.npz' % (MODEL_NAME, int(step)))
 
 
-def save_checkpoint(path, variables, global_step=0, adam_m=None, adam_v=None):
+def save_checkpoint(path, variables, global_step=0, adam_m=None, adam_v=None, adam_t=None):
     """variables / adam_m / adam_v: {TF name: tensor}.  Writes atomically (tmp + rename) and updates the directory index."""
     arrays = {k: v.detach().cpu().numpy() for k, v in variables.items()}
     arrays['global_step'] = np.asarray(int(global_step), dtype=np.int64)
+    if adam_t is not None and adam_m is not None:
+        arrays['adam_t'] = np.asarray(int(adam_t), dtype=np.int64)
     for slot, d in (('Adam', adam_m), ('Adam_1', adam_v)):
         if d is not None:
             for k, v in d.items():
@@ -74,7 +89,8 @@ class Restorer(object):
         with torch.no_grad():
             for k in self.var_names:
                 store.vars[k].copy_(torch.from_numpy(np.asarray(saved[k])).to(store.vars[k].device, torch.float32))
-        return int(saved['global_step']) if 'global_step' in saved else 0
+        k = global_step_key(saved)
+        return int(saved[k]) if k else 0
 
 
 def optimistic_restorer(save_file, store, vars_all=None):

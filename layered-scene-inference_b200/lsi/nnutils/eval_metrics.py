@@ -10,6 +10,8 @@ Restated quirk (ldi_pred_eval.py:402-405): the `> 0.95` threshold lands on the f
 disocclusion weights actually used are the un-thresholded AREA averages.
 """
 import numpy as np
+import math
+
 import torch
 
 from lsi.geometry import ldi as ldi_utils
@@ -45,7 +47,9 @@ def metrics_from_renders(opts, renders, imgs, gt_disps=None, disocc_masks=None):
             valid = torch.ones(B, H, W, 1, dtype=img.dtype, device=img.device)
         valid = (_area(valid, h_t, w_t) > 0.95).to(img.dtype)[..., 0]                  # ignore pixels that might have aliasing
         pw = (_area(img, h_t, w_t) - recons).abs().mean(dim=4).min(dim=0).values
-        x_min, y_min = int(round(w_t * opts.splat_bdry_ignore)), int(round(h_t * opts.splat_bdry_ignore))
+        # Python-2 round() (the reference's interpreter) rounds halves away from zero, as does the CUDA photo-loss kernel's floor(x + 0.5);
+        # Python-3 round() would round halves to even
+        x_min, y_min = int(math.floor(w_t * opts.splat_bdry_ignore + 0.5)), int(math.floor(h_t * opts.splat_bdry_ignore + 0.5))
         centre = torch.zeros(B, h_t, w_t, dtype=img.dtype, device=img.device)
         centre[:, y_min:h_t - y_min, x_min:w_t - x_min] = 1
         centre = centre * valid

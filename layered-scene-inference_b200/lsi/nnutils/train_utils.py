@@ -15,6 +15,7 @@ fused Adam step on the flat parameter buffer with the gradients scaled by 1/worl
 import os
 import types
 
+import numpy as np
 import torch
 
 from lsi import _b200
@@ -99,6 +100,8 @@ class HostViewPipeline(object):
     def __init__(self, opts, store, render_kw, batch, height, width, device, depth=2):
         from lsi.geometry import ldi as ldi_utils
         self._render = ldi_utils.forward_splat
+        if depth < 2:      # upload(k+1) is issued before batch k's kernels: with one slot it would overwrite batch k's inputs
+            raise ValueError('HostViewPipeline needs depth >= 2, got %d' % depth)
         self.opts, self.store, self.kw, self.device, self.depth = opts, store, dict(render_kw), torch.device(device), depth
         ds = float(render_kw.get('trg_downsampling', 1))
         ht, wt = int(height * ds), int(width * ds)
@@ -181,9 +184,13 @@ class Trainer(object):
         self.opts = opts
         self.store = store if store is not None else nets.ParamStore(seed=0)
         self.group = group
-        self.step_count = 0
+        self.step_count = 0          # global_step (train_utils.py:107-116)
+        self.adam_t = 0              # Adam's own step count (bias correction); restarts whenever the slots are not restored
         self.m = self.v = None
         self._built = False
+        self._deferred = None        # optimistic restore waiting for the variables to exist
+        self._pending_slots = None   # Adam slots read from a checkpoint before m / v were allocated
+        self._probe = None
 
     def define_pred_graph(self, imgs_src, imgs_trg):
         """ldi_enc_dec.py:175-228: both towers share their variables (reuse=True for the second)."""
@@ -213,57 +220,117 @@ class Trainer(object):
 
     def save(self, checkpoint_dir, step):
         """train_utils.py:224-232: step == 'latest' -> model.latest, else model-<global_step>.  Variables under their TF
-        names, global_step and the Adam slots."""
+        names, global_step, and (beyond the reference, for exact resume) the Adam slots with Adam's step count."""
         m, v = self._adam_slots()
-        return ckpt.save_checkpoint(ckpt.checkpoint_path(checkpoint_dir, step), self.store.vars, self.step_count, m, v)
+        return ckpt.save_checkpoint(ckpt.checkpoint_path(checkpoint_dir, step), self.store.vars, self.step_count, m, v,
+                                    adam_t=self.adam_t)
+
+    def _take_slots(self, saved):
+        """Adam slots of a checkpoint: applied now if m / v exist, else stashed until train_step allocates them.  Without
+        slots in the file Adam restarts (adam_t = 0), as the reference's does after any restore (its Saver keeps
+        neither the slots nor the beta powers)."""
+        names = [k for k in self.store.vars if k + '/Adam' in saved and k + '/Adam_1' in saved]
+        if not names or len(names) != len(self.store.vars):
+            self._pending_slots, self.adam_t = None, 0
+            if self.m is not None:
+                self.m.zero_()
+                self.v.zero_()
+            return
+        self.adam_t = int(saved['adam_t']) if 'adam_t' in saved else int(saved.get('global_step', 0))
+        self._pending_slots = {k: (saved[k + '/Adam'], saved[k + '/Adam_1']) for k in names}
+        self._apply_pending_slots()
+
+    def _apply_pending_slots(self):
+        m, v = self._adam_slots()
+        if m is None or self._pending_slots is None:
+            return
+        with torch.no_grad():
+            for k, (sm, sv) in self._pending_slots.items():
+                m[k].copy_(torch.from_numpy(sm).to(m[k].device))
+                v[k].copy_(torch.from_numpy(sv).to(v[k].device))
+        self._pending_slots = None
 
     def restore(self, path):
-        """saver.restore (train_utils.py:195): every variable must be present; resumes global_step and the Adam slots."""
+        """saver.restore (train_utils.py:195): every model variable must be present in the file with its shape.  On a Trainer
+        whose variables do not exist yet (they are created by the first forward) the variables are created FROM the
+        checkpoint, so that a resume can never silently keep a random initialisation.  Resumes global_step and, when the file
+        has them, the Adam slots."""
+        saved = ckpt.read_checkpoint(path)
+        model_keys = [k for k in saved if k not in ckpt.NON_VARIABLE_KEYS and not k.endswith('/Adam') and not k.endswith('/Adam_1')]
+        missing_in_store = [k for k in model_keys if k not in self.store.vars]
+        if missing_in_store:
+            if self.store.flat is not None:
+                raise RuntimeError('checkpoint %s has variables the (already flattened) model lacks: %s' % (path, missing_in_store[:5]))
+            self.store.load_state_dict({k: torch.from_numpy(np.asarray(saved[k])) for k in missing_in_store})
         r = ckpt.optimistic_restorer(path, self.store)
         if r.new_vars or r.shape_mismatch:
             raise RuntimeError('checkpoint %s does not match the model: missing %s, shape mismatch %s'
                                % (path, r.new_vars[:5], r.shape_mismatch[:5]))
         self.step_count = r.restore(self.store)
-        saved = ckpt.read_checkpoint(path)
-        m, v = self._adam_slots()
-        if m is not None:
-            with torch.no_grad():
-                for k in m:
-                    if k + '/Adam' in saved and k + '/Adam_1' in saved:
-                        m[k].copy_(torch.from_numpy(saved[k + '/Adam']).to(m[k].device))
-                        v[k].copy_(torch.from_numpy(saved[k + '/Adam_1']).to(v[k].device))
+        self._deferred = None
+        self._take_slots(saved)
         return self.step_count
 
     def init_from_checkpoints(self, checkpoint_dir, pretrain_name=None, pretrain_iter=0):
         """train_utils.py:176-200: resume from the latest checkpoint of checkpoint_dir if there is one; otherwise, with
         pretrain_name, optimistically restore <checkpoint_dir>/../<pretrain_name>/model-<pretrain_iter> (variables that
-        exist there with the same shape; the rest keep their initialisation).  Returns what happened."""
+        exist there with the same shape; the rest keep their initialisation).  Returns what happened.  The optimistic
+        restore of a Trainer whose variables do not exist yet is applied as soon as the first forward has created them."""
         latest = ckpt.latest_checkpoint(checkpoint_dir)
         if latest is not None:
             self.restore(latest)
             return 'resumed', latest
         if pretrain_name:
             path = ckpt.checkpoint_path(os.path.normpath(os.path.join(checkpoint_dir, '..', pretrain_name)), pretrain_iter)
-            r = ckpt.optimistic_restorer(path, self.store)
-            self.step_count = r.restore(self.store)
+            saved = ckpt.read_checkpoint(path)
+            self.step_count = int(saved[ckpt.global_step_key(saved)]) if ckpt.global_step_key(saved) else 0
+            self.adam_t, self._pending_slots = 0, None        # a pretrained net starts a new optimisation (reference: slots are never saved)
+            if not self.store.vars:
+                self._deferred = path
+            else:
+                ckpt.optimistic_restorer(path, self.store).restore(self.store)
             return 'pretrained', path
         return 'fresh', None
 
-    def train_step(self, batch):
-        """forward -> loss -> backward -> all-reduce(sum) of the flat gradients -> Adam.  Returns (total_loss, parts)."""
+    def _build_variables(self, batch):
+        """Create every variable once (one no-grad forward), apply a deferred optimistic restore, flatten, allocate Adam slots."""
+        with torch.no_grad():
+            self.define_pred_graph(batch['imgs_src'][:1], batch['imgs_trg'][:1])
+        if self._deferred is not None:
+            ckpt.optimistic_restorer(self._deferred, self.store).restore(self.store)
+            self._deferred = None
+        flat, _ = self.store.flatten()
+        self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self._apply_pending_slots()
+
+    def train_step(self, batch, dp_check=False):
+        """forward -> loss -> backward -> all-reduce(sum) of the flat gradients -> Adam.  Returns (total_loss, parts); with
+        dp_check=True also a dict proving the collective: <sum over ranks of the shard gradients, r> against <all-reduced
+        gradient, r> for a fixed random vector r (identical on every rank)."""
         if self.store.flat is None:
-            with torch.no_grad():                    # create every variable once, then flatten
-                self.define_pred_graph(batch['imgs_src'][:1], batch['imgs_trg'][:1])
-            flat, _ = self.store.flatten()
-            self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+            self._build_variables(batch)
         self.store.zero_grad()
         ldi_src, ldi_trg = self.define_pred_graph(batch['imgs_src'], batch['imgs_trg'])
         total, parts = self.define_loss_graph(ldi_src, ldi_trg, batch)
         total.backward()
-        world = allreduce_sum_(self.store.flat_grad, self.group)
+        chk = None
+        g = self.store.flat_grad
+        if dp_check:
+            if self._probe is None or self._probe.numel() != g.numel():
+                gen = torch.Generator(device=g.device)
+                gen.manual_seed(1234)
+                self._probe = torch.randn(g.numel(), device=g.device, generator=gen)
+            shard = torch.dot(g.double(), self._probe.double()).reshape(1)
+            allreduce_sum_(shard, self.group)
+        world = allreduce_sum_(g, self.group)
+        if dp_check:
+            chk = {'proj_sum_of_shards': float(shard), 'proj_allreduced': float(torch.dot(g.double(), self._probe.double())),
+                   'world': world}
         self.step_count += 1
+        self.adam_t += 1
         o = self.opts
         _b200.call('lsi_b200_adam_step', _b200.ptr(self.store.flat), _b200.ptr(self.store.flat_grad), _b200.ptr(self.m),
-                   _b200.ptr(self.v), self.store.flat.numel(), o.learning_rate, o.beta1, 0.999, 1e-8, self.step_count,
+                   _b200.ptr(self.v), self.store.flat.numel(), o.learning_rate, o.beta1, 0.999, 1e-8, self.adam_t,
                    1.0 / world, _b200.stream())
-        return total.detach(), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in parts.items()}
+        out = (total.detach(), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in parts.items()})
+        return out + (chk,) if dp_check else out

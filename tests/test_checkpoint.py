@@ -100,3 +100,70 @@ def test_trainer_resume_protocol(tmp_path):
     # a checkpoint that does not match the model is an error for the strict restore
     with pytest.raises(RuntimeError):
         train_utils.Trainer(opts, store=_store(1, VARS)).restore(ck.checkpoint_path(str(tmp_path / 'other'), 7))
+
+
+def test_resume_into_fresh_trainer_creates_variables_from_the_checkpoint(tmp_path):
+    """A Trainer whose variables do not exist yet (they are created by the first forward) must come out of a strict resume with
+    the SAVED weights -- not report success and later random-initialise them -- and Adam's slots / step count must survive."""
+    from lsi.nnutils import checkpoint as ck
+    from lsi.nnutils import train_utils
+    opts = train_utils.default_opts()
+    run = str(tmp_path / 'run')
+    tr = train_utils.Trainer(opts, store=_store(1, VARS))
+    flat, _ = tr.store.flatten()
+    tr.m, tr.v = torch.rand_like(flat), torch.rand_like(flat)
+    tr.step_count, tr.adam_t = 500, 321
+    tr.save(run, 500)
+    fresh = train_utils.Trainer(opts)                           # default ParamStore, no variables
+    fresh.store = __import__('lsi.nnutils.nets', fromlist=['x']).ParamStore(device='cpu', seed=99)
+    assert not fresh.store.vars
+    assert fresh.init_from_checkpoints(run)[0] == 'resumed' and fresh.step_count == 500 and fresh.adam_t == 321
+    assert sorted(fresh.store.vars) == sorted(n for n, _ in VARS)
+    for n, _ in VARS:
+        assert torch.equal(fresh.store.vars[n].detach(), tr.store.vars[n].detach())
+    # the slots wait until train_step allocates m / v (here: done by hand), then land in them
+    assert fresh.m is None and fresh._pending_slots is not None
+    flat2, _ = fresh.store.flatten()
+    fresh.m, fresh.v = torch.zeros_like(flat2), torch.zeros_like(flat2)
+    fresh._apply_pending_slots()
+    assert torch.equal(fresh.m, tr.m) and torch.equal(fresh.v, tr.v)
+    # a checkpoint without slots (the reference's own snapshots): Adam restarts at t = 0 with zero slots
+    ck.save_checkpoint(ck.checkpoint_path(str(tmp_path / 'ref'), 7), tr.store.vars, global_step=7)
+    again = train_utils.Trainer(opts, store=_store(5, VARS))
+    f3, _ = again.store.flatten()
+    again.m, again.v, again.adam_t = torch.ones_like(f3), torch.ones_like(f3), 40
+    again.restore(ck.checkpoint_path(str(tmp_path / 'ref'), 7))
+    assert again.step_count == 7 and again.adam_t == 0 and float(again.m.abs().max()) == 0 and float(again.v.abs().max()) == 0
+
+
+def test_deferred_pretrain_restore_and_tf_step_alias(tmp_path):
+    """Optimistic (pretrained-net) restore into a Trainer without variables is applied once the variables exist; a converted TF-1
+    snapshot names its counter 'train_op/global_step' (train_utils.py:107-116)."""
+    import numpy as np
+    from lsi.nnutils import checkpoint as ck
+    from lsi.nnutils import nets, train_utils
+    opts = train_utils.default_opts()
+    pre = _store(11, VARS[:2])
+    arrays = {k: v.detach().numpy() for k, v in pre.vars.items()}
+    arrays['train_op/global_step'] = np.asarray(4000, dtype=np.int64)
+    os.makedirs(str(tmp_path / 'pre'))
+    np.savez(ck.checkpoint_path(str(tmp_path / 'pre'), 4000), **arrays)
+    tr = train_utils.Trainer(opts, store=nets.ParamStore(device='cpu', seed=3))
+    what, _ = tr.init_from_checkpoints(str(tmp_path / 'run'), pretrain_name='pre', pretrain_iter=4000)
+    assert what == 'pretrained' and tr.step_count == 4000 and tr.adam_t == 0 and tr._deferred is not None
+
+    def fake_forward(a, b):                                       # stands for the first forward, which creates the variables
+        for n, shp in VARS:
+            tr.store.get(n, shp, reuse=False, kind='weights' if len(shp) == 4 else 'beta')
+    tr.define_pred_graph = fake_forward
+    keep = None
+    tr._build_variables({'imgs_src': torch.zeros(1, 1), 'imgs_trg': torch.zeros(1, 1)})
+    assert tr._deferred is None and tr.store.flat is not None
+    assert torch.equal(tr.store.vars[VARS[0][0]].detach(), pre.vars[VARS[0][0]].detach())      # restored
+    assert tr.store.vars[VARS[2][0]].abs().sum() > 0                                            # kept its initialisation
+
+
+def test_host_view_pipeline_rejects_depth_one():
+    from lsi.nnutils import train_utils
+    with pytest.raises(ValueError, match='depth >= 2'):
+        train_utils.HostViewPipeline(None, None, {}, 1, 8, 8, 'cpu', depth=1)

@@ -12,7 +12,9 @@ def main(src, dst):
     reader = tf.train.load_checkpoint(src)
     arrays = {}
     for name in reader.get_variable_to_shape_map():
-        arrays[name] = reader.get_tensor(name)       # TF names are kept verbatim, incl. <var>/Adam, <var>/Adam_1, global_step
+        arrays[name] = reader.get_tensor(name)       # TF names are kept verbatim.  The reference's Saver holds the model variables and the
+        # step counter only (train_utils.py:172-174) -- the latter as 'train_op/global_step', which lsi.nnutils.checkpoint accepts --
+        # and no Adam slots: after loading such a file Adam restarts, exactly as in the reference
     np.savez(dst, **arrays)
     print('wrote %d arrays to %s' % (len(arrays), dst))
 
