@@ -39,7 +39,7 @@ constexpr int kTH = 16, kTW = 8, kTileM = kTH * kTW;   // 128 output pixels = 12
 constexpr int kKC = 32;                                // fp32 channels per 128-byte row
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;                          // warp 0 TMA, 1 MMA, 2-5 epilogue, 6-9 transform
-constexpr int kThreadsWide = 576;                      // 1-CTA/SM variant: 8 epilogue warps (2-9: two sets taking alternate tiles = TMEM buffers), 8 transform warps (10-17)
+constexpr int kThreadsWide = 448;                      // 1-CTA/SM variant: 8 transform warps (6-13); its split flavour uses the kThreadsAll layout
 constexpr int kThreadsAll = 576;                       // all-phase variant: 8 epilogue warps (2-9, two per TMEM lane group), 8 transform warps (10-17)
 constexpr int kStgPitch = 36;                          // floats per staged pixel (144 B: conflict-free 128-bit rows)
 constexpr int kMaxCin = 128;
@@ -58,9 +58,8 @@ struct HaloParams {
   int in_f16;                // 1: the input tensor is stored as fp16 (RAW output of a producer run with out_f16): 64-byte rows,
                              //    64B swizzle, normalised in place by the transform warps (implies f16)
   int out_f16;               // 1: the RAW output is stored as fp16 (its only consumer normalises on load and feeds fp16 MMAs anyway)
-  int split_l;               // split, variant L: 64-byte filter rows (Whi ; Wlo), a_hi x both with N' = 2N, then a_lo x Whi with N' = N
-  int split;                 // 1: split fp16-pair activations and weights (split.cuh): 128-byte rows [hi 32 ch | lo 32 ch], kind::f16 MMAs over
-                             //    K = 64 against doubled filter tiles, two accumulators (columns [0,N) and [N,2N)); out_f16 == 2 stores split pairs
+  int split;                 // (= kSplit) split fp16-pair activations (128-byte rows [hi 32 ch | lo 32 ch]) and weights (2N rows of 64 bytes: Whi ; Wlo):
+                             //    a_hi x both with N' = 2N, then a_lo x Whi with N' = N; two accumulators (columns [0,N) and [N,2N)); out_f16 == 2 stores split pairs
   int all_phase;             // 1 (kAll): one CTA computes all stride^2 output phases of an up-conv tile from ONE halo load/transform
   int oy_min, ox_min;        // kAll: halo origin relative to the tile origin (minimum over the phases)
   int halo_w, halo_h;
@@ -342,8 +341,11 @@ __device__ __forceinline__ PhaseGeom phase_geom(const HaloParams& p, int s, int 
 //        normalised once instead of once per phase (that redundancy was ~45 % of the shared-memory traffic of upcnv1);
 //        the whole 16-tap filter bank is resident, one 32-column accumulator per phase.  Like kWide it runs one CTA per SM
 //        with 8 transform warps.
-template <bool kWide, bool kAll>
-__global__ void __launch_bounds__(kAll ? kThreadsAll : (kWide ? kThreadsWide : kThreads), (kWide || kAll) ? 1 : 2)
+// kSplit: split fp16-pair activations / weights (split.cuh, variant L: 64-byte filter rows Whi ; Wlo), two accumulators; its wide
+//        variant runs 8 epilogue warps (two sets taking alternate tiles = alternate TMEM buffers) because the split epilogue
+//        (second tcgen05.ld, combine, hi/lo packing) is twice as long.  Compile-time so that the other paths keep their code.
+template <bool kWide, bool kAll, bool kSplit>
+__global__ void __launch_bounds__((kAll || (kWide && kSplit)) ? kThreadsAll : (kWide ? kThreadsWide : kThreads), (kWide || kAll) ? 1 : 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -369,6 +371,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   // phase of this CTA (up-conv / data-gradient mode: one of stride^2 output phases; plain conv: the only one)
   constexpr bool kBig = kWide || kAll;
+  constexpr bool kEpi8 = kAll || (kWide && kSplit);   // 8 epilogue warps (2-9), transform warps from warp 10
   const int s = (p.mode == 1) ? p.stride : 1;
   const int G = kAll ? 1 : s * s;
   const int n_ph = kAll ? s * s : 1;           // phases computed per tile by this CTA
@@ -381,10 +384,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int oy_off = kAll ? p.oy_min : ((p.mode == 0) ? -p.pad_t : (py + p.pad_t - (ky0 + (nky - 1) * s)) / s);
   const int ox_off = kAll ? p.ox_min : ((p.mode == 0) ? -p.pad_l : (px + p.pad_l - (kx0 + (nkx - 1) * s)) / s);
 
-  const int n_mma = p.split ? 2 * p.n_tile : p.n_tile;   // UMMA N (split: D0 in columns [0, n_tile), D1 in [n_tile, 2 n_tile))
-  const int cm = p.split ? 2 : 1;                         // fp16 elements per channel in the activation tensor maps of the split layout
-  const int cmw = (p.split && !p.split_l) ? 2 : 1;        // ... and in the filter map (variant S)
-  const uint32_t rbw = (p.f16 || p.split_l) ? 64u : 128u; // bytes of one filter row
+  const int n_mma = kSplit ? 2 * p.n_tile : p.n_tile;    // UMMA N (split: D0 in columns [0, n_tile), D1 in [n_tile, 2 n_tile))
+  const int cm = kSplit ? 2 : 1;                          // fp16 elements per channel in the activation tensor maps of the split layout
+  const uint32_t rbw = (p.f16 || kSplit) ? 64u : 128u;    // bytes of one filter row
   const uint32_t acc_cols = kAll ? 32u * (uint32_t)(s * s) : (n_mma <= 32 ? 32u : (n_mma <= 64 ? 64u : 128u));
   const uint32_t tmem_cols = acc_cols * 2;
 
@@ -429,7 +431,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int i = 0; i < nky; ++i)
           for (int j = 0; j < nkx; ++j)
             for (int ch = 0; ch < p.chunks; ++ch)
-              tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC * cmw,
+              tma_load_2d(smem_u32(s_w) + (uint32_t)((i * nkx + j) * p.chunks + ch) * p.b_tap_bytes, &map_w, wfull, ch * kKC,
                           ((ky0 + i * s) * p.kw + (kx0 + j * s)) * n_mma);
       }
       Ring r(p.stages);
@@ -450,13 +452,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // ---------------- MMA issuer ----------------
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, K-major both, N>>3, M>>4
       // (kind::f16: A/B format F16 = 0, two K = 16 steps per 32-channel chunk)
-      const uint32_t idesc = (p.f16 || p.split) ? ((1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
+      const uint32_t idesc = (p.f16 || kSplit) ? ((1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24))
                                    : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24));
       // fp16-stored input: 64-byte rows with the 64B swizzle, 8-row groups halo_w rows apart; same shifted-start trick
       const uint32_t row_b = p.in_f16 ? 64u : 128u;
       const uint64_t hi_a = p.in_f16 ? (((uint64_t)1 << 16) | ((uint64_t)(((uint32_t)p.halo_w * 64u) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61))
                                      : umma_desc_hi((uint32_t)p.halo_w * 128u);
-      const uint64_t hi_b = (p.f16 || p.split_l) ? umma_desc_hi_sw64() : umma_desc_hi(1024u);
+      const uint64_t hi_b = (p.f16 || kSplit) ? umma_desc_hi_sw64() : umma_desc_hi(1024u);
       const uint32_t idesc_n = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);   // variant L: a_lo x Whi, N' = N
       mbar_wait(wfull, 0);
       const uint64_t b_desc0 = umma_desc(hi_b, smem_u32(s_w));
@@ -522,7 +524,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tp = 0; tp < 9; ++tp) {
               if (tp < ntaps) {
                 const uint64_t ad = a_desc0 + (uint64_t)a_tap[tp], bd = b_desc0 + (uint64_t)(b_tap[tp] + ch_off);
-                if (p.split_l) {                           // a_hi x (Whi ; Wlo) into columns [0, 2N), a_lo x Whi into [N, 2N)
+                if (kSplit) {                              // a_hi x (Whi ; Wlo) into columns [0, 2N), a_lo x Whi into [N, 2N)
 #pragma unroll
                   for (int kk = 0; kk < 2; ++kk) {
                     umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
@@ -531,12 +533,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                   for (int kk = 0; kk < 2; ++kk)
                     umma_f16(tmem_d + (uint32_t)p.n_tile, ad + 4 + 2 * kk, bd + 2 * kk, idesc_n, 1u);
-                } else if (p.split) {                      // K = 64 fp16 per 128-byte row: [hi | lo] x ([Whi | 0] ; [Wlo | Whi])
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) {
-                    umma_f16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, acc);
-                    acc = 1;
-                  }
                 } else if (p.f16) {
 #pragma unroll
                   for (int kk = 0; kk < kKC / 16; ++kk) {  // UMMA K = 16 for fp16: 32 bytes along the row
@@ -558,10 +554,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         umma_commit(&tmem_full[buf]);              // accumulator complete
       }
     }
-  } else if (warp < (kBig ? 10 : 6)) {
+  } else if (warp < (kEpi8 ? 10 : 6)) {
     // ---------------- epilogue: TMEM -> registers -> staging -> global ----------------
     const int lg = warp & 3;                     // TMEM lane group this warp may access
-    const int eset = kBig ? ((warp - 2) >> 2) : 0;   // two warps per lane group: kAll -- each takes every other phase; kWide -- every other tile
+    const int eset = kEpi8 ? ((warp - 2) >> 2) : 0;   // two warps per lane group: kAll -- each takes every other phase; kWide -- every other tile
     const int row = lg * 32 + lane;              // A-tile row = pixel within the 16 x 8 patch
     const int hy = row >> 3, wx = row & 7;
     float* stg = staging + (size_t)(eset * 4 + lg) * 32 * kStgPitch;
@@ -574,7 +570,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ++tcount, ti.next()) {
       const int n_img = ti.n, y0 = ti.ty * kTH, x0 = ti.tx * kTW;
       const int buf = tcount & 1;
-      if (kWide && buf != eset) continue;        // this tile's accumulator buffer belongs to the other set of epilogue warps
+      if (kWide && kSplit && buf != eset) continue;        // this tile's accumulator buffer belongs to the other set of epilogue warps
       mbar_wait(&tmem_full[buf], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool in_range = (y0 + hy) < p.Hp && (x0 + wx) < p.Wp;
@@ -601,7 +597,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j = 16; j < 32; ++j) r[j] = 0u;
         }
-        if (!kAll && p.split) {   // second accumulator (cross terms, scaled by 2^11): columns [n_tile + cc, ...)
+        if (kSplit) {   // second accumulator (cross terms, scaled by 2^11): columns [n_tile + cc, ...)
           uint32_t r1[32];
           const uint32_t taddr1 = taddr + (uint32_t)p.n_tile;
           if (p.n_tile - cc >= 32) {
@@ -680,7 +676,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (oy < p.Hp && ox < p.Wp) {
             if (p.mode == 1) { oy = oy * s + e_py; ox = ox * s + e_px; }
             const size_t e = ((size_t)(n_img * p.Ho + oy) * p.Wo + ox) * p.out_cs + cc + c4;
-            if (p.out_f16 == 2) {   // split pairs: this chunk's 128 bytes = [hi 32 ch | lo 32 ch] at the fp32 tensor's chunk address
+            if (kSplit && p.out_f16 == 2) {   // split pairs: this chunk's 128 bytes = [hi 32 ch | lo 32 ch] at the fp32 tensor's chunk address
               uint2 h2, l2;
               split_pack2(v.x, v.y, h2.x, l2.x); split_pack2(v.z, v.w, h2.y, l2.y);
               uint8_t* cb = reinterpret_cast<uint8_t*>(p.out + (e - c4)) + c4 * 2;
@@ -701,7 +697,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (p.stat_part) {
-      float* my_part = p.stat_part + ((size_t)blockIdx.x * (kBig ? 8 : 4) + eset * 4 + lg) * p.n_tile * 2;
+      float* my_part = p.stat_part + ((size_t)blockIdx.x * (kEpi8 ? 8 : 4) + eset * 4 + lg) * p.n_tile * 2;
 #pragma unroll
       for (int i = 0; i < (kWide ? 2 : 1); ++i) {
         const float4 fs = i ? ssum1 : ssum0, fq = i ? ssq1 : ssq0;
@@ -720,7 +716,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (bn_in) {
     // ---------------- transform: producer's batch-norm + ReLU applied to the halo tile in shared memory ----------------
-    const int tid = threadIdx.x - (kBig ? 320 : 192);
+    const int tid = threadIdx.x - (kEpi8 ? 320 : 192);
     Ring r(p.stages);
     TileIter ti(cta_in_group, ctas_per_group, p.tiles_x, p.per_img);
     for (int t = cta_in_group; t < p.spatial_tiles; t += ctas_per_group, ti.next()) {
@@ -731,7 +727,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float4* tile = reinterpret_cast<float4*>(s_a + (size_t)r.st * stage_bytes);
         const float* ta = bn_a + ch * kKC; const float* tb = bn_b + ch * kKC;
         constexpr int kNT = kBig ? 256 : 128;
-        if (p.split) {
+        if (kSplit) {
           if (interior) transform_tile_s<true, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
           else transform_tile_s<false, kNT>(reinterpret_cast<uint4*>(tile), ta, tb, tid, p, ys0, xs0);
         } else if (p.in_f16) {
@@ -781,23 +777,6 @@ __global__ void __launch_bounds__(256) halo_prep_weights_f16_kernel(const float*
   }
 }
 
-// split mode (split.cuh): [tap][half][n][chunk][64 fp16]; half 0 rows = [w_hi | 0], half 1 rows = [w_lo | w_hi]
-__global__ void __launch_bounds__(256) halo_prep_weights_split_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
-                                                                      int cout, int n_tile, int w_tap, int w_ci, int w_co) {
-  const long long total = (long long)taps * 2 * n_tile * 2 * cin;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % (2 * cin));
-    const long long row = i / (2 * cin);
-    const int ci = (k >> 6) * 32 + (k & 31), part = (k >> 5) & 1;
-    const int tap = (int)(row / (2 * n_tile)), r2 = (int)(row % (2 * n_tile));
-    const int half = r2 / n_tile, co = r2 % n_tile;
-    const float v = (co < cout) ? w[(size_t)tap * w_tap + (size_t)ci * w_ci + (size_t)co * w_co] : 0.f;
-    const __half hi = __float2half_rn(fminf(fmaxf(v, -kSplitMax), kSplitMax));
-    const __half lo = __float2half_rn((v - __half2float(hi)) * kSplitScale);
-    wk[i] = half == 0 ? (part == 0 ? hi : __float2half_rn(0.f)) : (part == 0 ? lo : hi);
-  }
-}
-
 // split mode, variant L: [tap][half][n][cin] fp16; half 0 rows = w_hi, half 1 rows = w_lo
 __global__ void __launch_bounds__(256) halo_prep_weights_split_l_kernel(const float* __restrict__ w, __half* __restrict__ wk, int taps, int cin,
                                                                         int cout, int n_tile, int w_tap, int w_ci, int w_co) {
@@ -811,12 +790,6 @@ __global__ void __launch_bounds__(256) halo_prep_weights_split_l_kernel(const fl
     const __half hi = __float2half_rn(fminf(fmaxf(v, -kSplitMax), kSplitMax));
     wk[i] = half == 0 ? hi : __float2half_rn((v - __half2float(hi)) * kSplitScale);
   }
-}
-
-bool halo_split_variant_l() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("LSI_B200_SPLIT_VARIANT"); on = (e && (e[0] == 'S' || e[0] == 's')) ? 0 : 1; }
-  return on == 1;
 }
 
 __global__ void __launch_bounds__(256) halo_finalize_stats_kernel(const float* __restrict__ partial, int nparts, int n_pad, int C,
@@ -904,7 +877,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool
     w_taps = d->kh * d->kw;
   }
   pl->halo_bytes = ((uint32_t)(pl->halo_w * pl->halo_h) * (in_f16 ? 64u : 128u) + 1023u) & ~1023u;
-  pl->b_tap_bytes = ((uint32_t)pl->n_tile * (split ? (halo_split_variant_l() ? 128u : 256u) : (f16 ? 64u : 128u)) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows; split: 2 n_tile rows of 64 (L) / 128 (S) bytes
+  pl->b_tap_bytes = ((uint32_t)pl->n_tile * ((split || !f16) ? 128u : 64u) + 1023u) & ~1023u;   // fp16 weights: 64-byte rows; split: 2 n_tile rows of 64 (L) / 128 (S) bytes
   pl->w_bytes = (uint32_t)(w_taps * pl->chunks) * pl->b_tap_bytes;
   const size_t fixed4 = 1024 + pl->w_bytes + 256 + 2 * kMaxCin * sizeof(float) + 4 * 32 * kStgPitch * sizeof(float);
   const size_t fixed8 = fixed4 + 4 * 32 * kStgPitch * sizeof(float);      // 8 epilogue warps (all-phase and 1-CTA/SM wide variants)
@@ -917,7 +890,7 @@ bool halo_plan(const lsi_b200_conv_desc* d, HaloPlan* pl, bool f16 = false, bool
   if (force_ctas != 1 && !all_phase && pl->n_tile <= 32 && fixed + 2 * stage <= budget2) {   // the 64-column / all-phase variants are built for 1 CTA/SM
     pl->ctas_per_sm = 2;
     pl->stages = (int)((budget2 - fixed) / stage);
-  } else if ((fixed = ((all_phase || split || pl->n_tile > 32) ? fixed8 : fixed4)) + 2 * stage <= budget1) {
+  } else if ((fixed = ((all_phase || split) ? fixed8 : fixed4)) + 2 * stage <= budget1) {
     pl->ctas_per_sm = 1;
     pl->stages = (int)((budget1 - fixed) / stage);
   } else {
@@ -1004,7 +977,7 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   p.per_img = p.tiles_x * tiles_y; p.spatial_tiles = p.per_img * d->batch;
   p.chunks = pl.chunks; p.chunks_a = c_in_a / kKC; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
   p.n_tile = pl.n_tile; p.epilogue = d->epilogue; p.stages = pl.stages; p.f16 = f16 ? 1 : 0; p.in_f16 = in_f16 ? 1 : 0; p.out_f16 = out_f16;
-  p.split = split ? 1 : 0; p.split_l = (split && halo_split_variant_l()) ? 1 : 0;
+  p.split = split ? 1 : 0;
   p.all_phase = pl.all_phase; p.oy_min = pl.oy_min; p.ox_min = pl.ox_min;
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
   p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
@@ -1015,11 +988,8 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   {
     const long long total = (long long)taps * pl.n_tile * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    if (split && p.split_l)
+    if (split)
       halo_prep_weights_split_l_kernel<<<(unsigned)(g * 2 > 148 * 8 ? 148 * 8 : g * 2), 256, 0, st>>>(
-          w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, pl.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
-    else if (split)
-      halo_prep_weights_split_kernel<<<(unsigned)(g * 4 > 148 * 8 ? 148 * 8 : g * 4), 256, 0, st>>>(
           w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, pl.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride);
     else if (f16)
       halo_prep_weights_f16_kernel<<<(unsigned)g, 256, 0, st>>>(w, reinterpret_cast<__half*>(wk), taps, d->c_in, d->c_out, pl.n_tile,
@@ -1047,23 +1017,25 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   if (in_b) { if (int rc = make_act_map(&map_b, in_b, d->c_in - c_in_a, in_b_c_stride)) return rc; }
   else map_b = map_a;
   {
-    const cuuint64_t cm = split ? 2 : 1, cmw = (split && !p.split_l) ? 2 : 1;
-    cuuint64_t dims[2] = {(cuuint64_t)d->c_in * cmw, (cuuint64_t)taps * pl.n_tile * cm};
-    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * ((f16 || p.split_l) ? 2 : 4)};
-    cuuint32_t box[2] = {(cuuint32_t)(kKC * cmw), (cuuint32_t)(pl.n_tile * cm)};
+    const cuuint64_t cm = split ? 2 : 1;   // split: 2 n_tile filter rows (Whi ; Wlo) of 32 fp16 channels per tap
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_in, (cuuint64_t)taps * pl.n_tile * cm};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c_in * ((f16 || split) ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)(pl.n_tile * cm)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_w, (f16 || split) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, wk, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, (f16 || p.split_l) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, (f16 || split) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return LSI_B200_ECUDA; }
   }
   const bool wide = pl.n_tile > 32 || (split && pl.ctas_per_sm == 1);   // the 448-thread variant: 1 CTA/SM, 8 transform warps
-  const int kv = pl.all_phase ? 2 : (wide ? 1 : 0);
-  static size_t smem_set[3] = {0, 0, 0};
+  const int kv = split ? (wide ? 4 : 3) : (pl.all_phase ? 2 : (wide ? 1 : 0));
+  static size_t smem_set[5] = {0, 0, 0, 0, 0};
   if (pl.smem > smem_set[kv]) {
-    if (kv == 2) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    else if (kv == 1) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    else LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    if (kv == 4) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else if (kv == 3) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else if (kv == 2) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else if (kv == 1) LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    else LSI_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     smem_set[kv] = pl.smem;
   }
   const int G = pl.all_phase ? 1 : s * s;
@@ -1077,13 +1049,15 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   }
   {
     ScopedTiming tm(kConvTc, st);
-    if (kv == 2) conv_halo_kernel<false, true><<<dim3((unsigned)n_ctas), kThreadsAll, pl.smem, st>>>(map_a, map_b, map_w, p);
-    else if (kv == 1) conv_halo_kernel<true, false><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_b, map_w, p);
-    else conv_halo_kernel<false, false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_b, map_w, p);
+    if (kv == 4) conv_halo_kernel<true, false, true><<<dim3((unsigned)n_ctas), kThreadsAll, pl.smem, st>>>(map_a, map_b, map_w, p);
+    else if (kv == 3) conv_halo_kernel<false, false, true><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_b, map_w, p);
+    else if (kv == 2) conv_halo_kernel<false, true, false><<<dim3((unsigned)n_ctas), kThreadsAll, pl.smem, st>>>(map_a, map_b, map_w, p);
+    else if (kv == 1) conv_halo_kernel<true, false, false><<<dim3((unsigned)n_ctas), kThreadsWide, pl.smem, st>>>(map_a, map_b, map_w, p);
+    else conv_halo_kernel<false, false, false><<<dim3((unsigned)n_ctas), kThreads, pl.smem, st>>>(map_a, map_b, map_w, p);
   }
   LSI_LAUNCH_CHECK();
   if (out_bn_stats) {
-    halo_finalize_stats_kernel<<<(d->c_out + 7) / 8, 256, 0, st>>>(p.stat_part, n_ctas * ((pl.all_phase || wide) ? 8 : 4), pl.n_tile, d->c_out,
+    halo_finalize_stats_kernel<<<(d->c_out + 7) / 8, 256, 0, st>>>(p.stat_part, n_ctas * ((pl.all_phase || kv == 4) ? 8 : 4), pl.n_tile, d->c_out,
                                                                   (long long)d->batch * d->h_out * d->w_out, bn_eps, out_bn_stats);
     LSI_LAUNCH_CHECK();
   }

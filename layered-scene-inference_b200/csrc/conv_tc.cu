@@ -194,6 +194,8 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile, int
 // Persistent CTAs: each loops over output tiles.  The TMA producer runs ahead across tile boundaries through the
 // shared-memory ring; the MMA issuer alternates between two TMEM accumulator buffers so that the epilogue warps drain
 // tile i while tile i+1 is being accumulated (small-K layers -- 3x3x32 -- are prologue/epilogue bound otherwise).
+// kSplit: the split-precision mode (p.h16 == 2 / 3) is compiled separately so that the TF32 / fp16 instantiation keeps its code
+template <bool kSplit>
 __global__ void __launch_bounds__(kThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -201,8 +203,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // carve: [stages][A 16 KB][B n_tile*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t rb = (p.h16 == 1) ? 64u : 128u; // bytes of one 32-channel activation row
-  const bool split = p.h16 >= 2;                 // 2: variant S (128-byte filter rows [Whi|0];[Wlo|Whi]), 3: variant L (64-byte filter rows Whi;Wlo)
-  const bool split_l = p.h16 == 3;
+  const bool split = kSplit;                     // p.h16 2: variant S (128-byte filter rows [Whi|0];[Wlo|Whi]), 3: variant L (64-byte filter rows Whi;Wlo)
+  const bool split_l = kSplit && p.h16 == 3;
   const int n_mma = split ? 2 * p.n_tile : p.n_tile;   // UMMA N (split: D0 = hi*Whi in columns [0,N), D1 = cross terms in [N,2N))
   const int cm = split ? 2 : 1;                  // fp16 elements per channel in the activation tensor maps of the split layout
   const int cmw = (p.h16 == 2) ? 2 : 1;          // ... and in the filter map (variant S only)
@@ -714,7 +716,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   const uint32_t b_bytes = ((uint32_t)n_mma * rbw + 1023) & ~1023u;
   // x-merge: unit-stride gathers with more than one tap along x, on images wide enough for 16x8 tiles to make sense
   const int nkx_max = (d->mode == 1) ? (d->kw + s - 1) / s : d->kw;
-  p.xm = (xmerge_enabled() && (d->mode == 1 || d->stride == 1) && nkx_max >= 2 && nkx_max <= 9 && p.Hp >= 16 && p.n_pad <= 128) ? 1 : 0;
+  p.xm = (xmerge_enabled() && (d->mode == 1 || d->stride == 1) && nkx_max >= 2 && nkx_max <= 9 && p.Hp >= 16) ? 1 : 0;
   if (p.xm) {   // at least two ring stages of (halo tile + one filter tile per tap along x) must fit
     const uint32_t hw = xmerge_tight() ? 8 + nkx_max - 1 : 16;
     if (2 * (hw * 16 * rb + (uint32_t)d->kw * b_bytes) > 200u * 1024u) p.xm = 0;
@@ -797,10 +799,12 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 256 + 1024 + (bn_stats ? 4 * 32 * 33 * sizeof(float) : 0);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  static size_t smem_set[2] = {0, 0};
+  const int ks = h16 >= 2 ? 1 : 0;
+  if (smem > smem_set[ks]) {
+    if (ks) LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else LSI_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[ks] = smem;
   }
   int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
   const int tmem_per_cta = 2 * (n_mma <= 32 ? 32 : n_mma <= 64 ? 64 : n_mma <= 128 ? 128 : 256);
@@ -818,7 +822,8 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   }
   {
     ScopedTiming tm(kConvTc, st);
-    conv_tc_kernel<<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
+    if (ks) conv_tc_kernel<true><<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
+    else conv_tc_kernel<false><<<grid, kThreads, smem, st>>>(map_a, map_b, map_w, p);
   }
   LSI_LAUNCH_CHECK();
   if (bn_stats) {
