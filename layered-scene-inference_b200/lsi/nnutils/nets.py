@@ -282,6 +282,7 @@ _HALO_F16_STORE = os.environ.get('LSI_B200_HALO_F16_STORE', '1') != '0'
 _STEM_TC = os.environ.get('LSI_B200_STEM_TC', '1') != '0'
 _HALO_CONCAT = os.environ.get('LSI_B200_HALO_CONCAT', '1') != '0'
 _OUT_SCALE_CACHE = {}
+_SPLIT_UPCONV_MATERIALIZE = os.environ.get('LSI_B200_SPLIT_UPCONV_MATERIALIZE', '1') != '0'
 
 
 def set_halo_mode(on):
@@ -497,6 +498,10 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
     fp32 CUDA-core kernels (TMA cannot address 12-byte pixels) and is packed afterwards."""
     pair = isinstance(x, (tuple, list))
     lib = _b200.lib()
+    if transposed and _SPLIT_UPCONV_MATERIALIZE and isinstance(x, _Pending):
+        # a 4x4/2 up-conv runs one CTA group per output phase: normalising on load would repeat the (ALU-heavy) split transform of
+        # every halo tile four times; one in-place pass over the input in HBM is cheaper
+        x = x.materialize()
     if not pair and (isinstance(x, _SplitAct) or (isinstance(x, _Pending) and isinstance(x.z, _SplitAct) and x._done is None)) \
             and _HALO and cout % 32 == 0:
         # full-resolution few-channel head layers: halo-tile kernel (resident filter bank, one TMA halo box per tile, a pending
