@@ -308,6 +308,14 @@ LSI_B200_API int lsi_b200_bn_relu_backward(const float* x, const float* y, const
                                            float* dbeta_sums, long long n_pixels, int channels, int x_c_stride,
                                            int y_c_stride, int dy_c_stride, int dx_c_stride, int relu, int accumulate,
                                            void* workspace, void* stream);
+/* lsi_b200_bn_relu_backward in two stages, for batch statistics that span several data-parallel ranks (the reference
+ * normalises over the whole batch on one device, nets.py:263-272): stage 1 writes this rank's (sum dz, sum dz*xhat) to
+ * dbeta_sums; the caller all-reduces them; stage 2 computes dx from the given sums with 1 / n_pixels_stat (global count). */
+LSI_B200_API int lsi_b200_bn_relu_backward_staged(const float* x, const float* y, const float* dy, const float* stats,
+                                                  float* dx, float* dbeta_sums, long long n_pixels, long long n_pixels_stat,
+                                                  int channels, int x_c_stride, int y_c_stride, int dy_c_stride,
+                                                  int dx_c_stride, int relu, int accumulate, int stage, void* workspace,
+                                                  void* stream);
 /* sums[c] = (sum_x, sum_x^2) over pixels (bias gradients of the prediction conv). */
 LSI_B200_API int lsi_b200_channel_sums(const float* x, float* sums, long long n_pixels, int channels, int x_c_stride,
                                        void* workspace, void* stream);

@@ -127,11 +127,12 @@ __global__ void __launch_bounds__(256) bn_apply_vec4_kernel(const BnApplyParams 
 struct BnBwdParams {
   const float* x; const float* y; const float* dy; const float* stats; const float* sums; float* dx;
   long long P; int C, x_cs, y_cs, dy_cs, dx_cs, relu, accumulate;
+  long long P_stat;      // pixels the statistics (and `sums`) were reduced over: P, or the global count under synchronised BN
 };
 
 __global__ void __launch_bounds__(256) bn_backward_kernel(const BnBwdParams p) {
   const long long total = p.P * p.C;
-  const float invP = 1.f / (float)p.P;
+  const float invP = 1.f / (float)p.P_stat;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long q = i / p.C; const int c = (int)(i - q * p.C);
     const float mean = __ldg(p.stats + 2 * c), invstd = __ldg(p.stats + 2 * c + 1);
@@ -388,7 +389,34 @@ extern "C" int lsi_b200_bn_relu_backward(const float* x, const float* y, const f
   LSI_LAUNCH_CHECK();
   finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, dbeta_sums);
   LSI_LAUNCH_CHECK();
-  BnBwdParams bp{x, y, dy, stats, dbeta_sums, dx, n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, dx_c_stride, relu, accumulate};
+  BnBwdParams bp{x, y, dy, stats, dbeta_sums, dx, n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, dx_c_stride, relu, accumulate, n_pixels};
+  bn_backward_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(bp);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+// The same in two stages, for batch norm whose statistics span several ranks (the reference normalises over the whole batch on
+// one device, nets.py:263-272): stage 1 reduces this rank's (sum dz, sum dz*xhat) into dbeta_sums; the caller all-reduces them;
+// stage 2 applies dx with the given sums and 1 / n_pixels_stat (the global pixel count).
+extern "C" int lsi_b200_bn_relu_backward_staged(const float* x, const float* y, const float* dy, const float* stats, float* dx,
+                                                float* dbeta_sums, long long n_pixels, long long n_pixels_stat, int channels,
+                                                int x_c_stride, int y_c_stride, int dy_c_stride, int dx_c_stride, int relu,
+                                                int accumulate, int stage, void* workspace, void* stream) {
+  LSI_REQUIRE(x && y && dy && stats && dbeta_sums && workspace, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && n_pixels_stat >= n_pixels && channels >= 1 && (stage == 1 || stage == 2), "bad sizes / stage");
+  cudaStream_t st = as_stream(stream);
+  if (stage == 1) {
+    const int nb = stat_blocks(n_pixels);
+    StatParams sp{x, y, dy, stats, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, 1, relu};
+    channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
+    LSI_LAUNCH_CHECK();
+    finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, dbeta_sums);
+    LSI_LAUNCH_CHECK();
+    return LSI_B200_OK;
+  }
+  LSI_REQUIRE(dx != nullptr, "NULL pointer argument");
+  BnBwdParams bp{x, y, dy, stats, dbeta_sums, dx, n_pixels, channels, x_c_stride, y_c_stride, dy_c_stride, dx_c_stride, relu, accumulate,
+                 n_pixels_stat};
   bn_backward_kernel<<<ew_grid(n_pixels * channels), 256, 0, st>>>(bp);
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;

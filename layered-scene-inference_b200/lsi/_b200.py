@@ -83,6 +83,7 @@ SIGNATURES = {
     'lsi_b200_conv2d_tc_bnstats': (_I, [_CP, _P, _I, _P, _I, _P, _P, _P, _F, _P, _SZ, _P]),
     'lsi_b200_bn_relu_forward': (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _F, _I, _I, _P, _P]),
     'lsi_b200_bn_relu_backward': (_I, [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'lsi_b200_bn_relu_backward_staged': (_I, [_P, _P, _P, _P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'lsi_b200_channel_sums': (_I, [_P, _P, _LL, _I, _I, _P, _P]),
     'lsi_b200_copy_channels': (_I, [_P, _P, _LL, _I, _I, _I, _I, _P]),
     'lsi_b200_sigmoid_backward': (_I, [_P, _P, _P, _LL, _P]),

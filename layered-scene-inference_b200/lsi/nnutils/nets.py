@@ -389,6 +389,28 @@ class _Geometry(object):
             self.w_shape = [4, 4, Cout, Cin]
 
 
+_SYNC_BN = None      # (process group or None for the default group) when batch-norm statistics span the data-parallel ranks
+
+
+def set_sync_bn(enabled, group=None):
+    """Synchronised batch norm for data-parallel training: the reference normalises over the whole batch on one device
+    (nets.py:263-272, ldi_enc_dec.py:198-201); with the batch sharded over ranks, per-replica statistics are a different
+    function.  When enabled, every training-path BN all-reduces its per-channel (sum, sum of squares) in the forward pass and
+    its (sum dz, sum dz*xhat) in the backward pass -- two [C,2] collectives per layer -- so that an N-rank step equals the
+    single-device step on the global batch.  No effect when torch.distributed is not initialised or world size is 1."""
+    global _SYNC_BN
+    _SYNC_BN = (group,) if enabled else None
+
+
+def _sync_bn_world():
+    if _SYNC_BN is None:
+        return None, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    return _SYNC_BN[0], dist.get_world_size(_SYNC_BN[0])
+
+
 class _ConvBNReLU(torch.autograd.Function):
     """slim.conv2d / slim.conv2d_transpose with normalizer_fn=batch_norm and activation relu (nets.py:263-272)."""
 
@@ -400,6 +422,19 @@ class _ConvBNReLU(torch.autograd.Function):
         have_stats = _conv(geo.fwd, x, w, z, bn_stats=stats)        # tensor-core path reduces the BN statistics in its epilogue
         y = torch.empty_like(z)
         P = geo.B * geo.Ho * geo.Wo
+        group, world = _sync_bn_world()
+        ctx.sync = (group, world)
+        if world > 1:            # statistics over the global batch: all-reduce (sum z, sum z^2), finish in fp64
+            import torch.distributed as dist
+            sums = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+            _b200.call('lsi_b200_channel_sums', _b200.ptr(z), _b200.ptr(sums), P, geo.Cout, geo.Cout,
+                       _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+            sums = sums.double()
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            mean = sums[:, 0] / (P * world)
+            var = (sums[:, 1] / (P * world) - mean * mean).clamp_min(0.0)
+            stats.copy_(torch.stack([mean, 1.0 / torch.sqrt(var + BN_EPS)], dim=1).float())
+            have_stats = True
         _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(y), _b200.ptr(stats), P, geo.Cout,
                    geo.Cout, geo.Cout, BN_EPS, 1, 1 if have_stats else 0, _b200.ptr(_bn_workspace(dev, geo.Cout)),
                    _b200.stream())
@@ -416,10 +451,20 @@ class _ConvBNReLU(torch.autograd.Function):
         P = geo.B * geo.Ho * geo.Wo
         dz = torch.empty_like(z)
         sums = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
-        _b200.call('lsi_b200_bn_relu_backward', _b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
-                   _b200.ptr(sums), P, geo.Cout, geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0,
-                   _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
-        dbeta = sums[:, 0].contiguous()
+        group, world = ctx.sync
+        if world > 1:            # (sum dz, sum dz*xhat) over the global batch; dbeta stays this rank's share (the gradient all-reduce sums it)
+            import torch.distributed as dist
+            args = (_b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz), _b200.ptr(sums), P, P * world, geo.Cout,
+                    geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0)
+            _b200.call('lsi_b200_bn_relu_backward_staged', *args, 1, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+            dbeta = sums[:, 0].contiguous()
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            _b200.call('lsi_b200_bn_relu_backward_staged', *args, 2, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        else:
+            _b200.call('lsi_b200_bn_relu_backward', _b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
+                       _b200.ptr(sums), P, geo.Cout, geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0,
+                       _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+            dbeta = sums[:, 0].contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
