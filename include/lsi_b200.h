@@ -319,6 +319,9 @@ LSI_B200_API int lsi_b200_bn_relu_backward_staged(const float* x, const float* y
 /* sums[c] = (sum_x, sum_x^2) over pixels (bias gradients of the prediction conv). */
 LSI_B200_API int lsi_b200_channel_sums(const float* x, float* sums, long long n_pixels, int channels, int x_c_stride,
                                        void* workspace, void* stream);
+/* The same with fp64 results (the sums that cross ranks under synchronised batch norm, lsi.nnutils.nets.set_sync_bn). */
+LSI_B200_API int lsi_b200_channel_sums_f64(const float* x, double* sums, long long n_pixels, int channels, int x_c_stride,
+                                           void* workspace, void* stream);
 /* dst[q][0..C) (+)= src[q][0..C) with independent pixel strides: tf.concat (nets.py:300,...) and its gradient. */
 LSI_B200_API int lsi_b200_copy_channels(const float* src, float* dst, long long n_pixels, int channels, int src_c_stride,
                                         int dst_c_stride, int accumulate, void* stream);

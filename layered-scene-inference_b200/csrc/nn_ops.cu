@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(256) finalize_stats_kernel(const double* __res
     double var = b / (double)P - mean * mean;
     if (var < 0.0) var = 0.0;
     out[2 * c] = (float)mean; out[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  } else if (mode == 2) {      // raw fp64 sums (synchronised batch norm: the ranks' sums are all-reduced before mean / variance)
+    reinterpret_cast<double*>(out)[2 * c] = a; reinterpret_cast<double*>(out)[2 * c + 1] = b;
   } else {
     out[2 * c] = (float)a; out[2 * c + 1] = (float)b;
   }
@@ -433,6 +435,23 @@ extern "C" int lsi_b200_channel_sums(const float* x, float* sums, long long n_pi
   channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
   LSI_LAUNCH_CHECK();
   finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 1, sums);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+// fp64 variant: sums[c] = (sum_x, sum_x^2) as doubles -- E[x^2] - mean^2 cancels catastrophically in fp32 for channels whose mean
+// dominates their spread, so the sums that cross ranks under synchronised batch norm stay in fp64
+extern "C" int lsi_b200_channel_sums_f64(const float* x, double* sums, long long n_pixels, int channels, int x_c_stride,
+                                         void* workspace, void* stream) {
+  LSI_REQUIRE(x && sums && workspace, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 1 && x_c_stride >= channels, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  const int nb = stat_blocks(n_pixels);
+  StatParams sp{x, nullptr, nullptr, nullptr, static_cast<double*>(workspace), n_pixels, channels, x_c_stride, 0, 0, 0, 0};
+  channel_stats_kernel<<<nb, 256, 0, st>>>(sp);
+  LSI_LAUNCH_CHECK();
+  finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), nb, channels, n_pixels, 0.f, 2,
+                                                           reinterpret_cast<float*>(sums));
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }

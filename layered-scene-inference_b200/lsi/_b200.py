@@ -85,6 +85,7 @@ SIGNATURES = {
     'lsi_b200_bn_relu_backward': (_I, [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'lsi_b200_bn_relu_backward_staged': (_I, [_P, _P, _P, _P, _P, _P, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'lsi_b200_channel_sums': (_I, [_P, _P, _LL, _I, _I, _P, _P]),
+    'lsi_b200_channel_sums_f64': (_I, [_P, _P, _LL, _I, _I, _P, _P]),
     'lsi_b200_copy_channels': (_I, [_P, _P, _LL, _I, _I, _I, _I, _P]),
     'lsi_b200_sigmoid_backward': (_I, [_P, _P, _P, _LL, _P]),
     'lsi_b200_area_resize_u8': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),

@@ -426,10 +426,9 @@ class _ConvBNReLU(torch.autograd.Function):
         ctx.sync = (group, world)
         if world > 1:            # statistics over the global batch: all-reduce (sum z, sum z^2), finish in fp64
             import torch.distributed as dist
-            sums = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
-            _b200.call('lsi_b200_channel_sums', _b200.ptr(z), _b200.ptr(sums), P, geo.Cout, geo.Cout,
+            sums = torch.empty(geo.Cout, 2, dtype=torch.float64, device=dev)
+            _b200.call('lsi_b200_channel_sums_f64', _b200.ptr(z), _b200.ptr(sums), P, geo.Cout, geo.Cout,
                        _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
-            sums = sums.double()
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
             mean = sums[:, 0] / (P * world)
             var = (sums[:, 1] / (P * world) - mean * mean).clamp_min(0.0)
