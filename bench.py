@@ -490,6 +490,13 @@ def main():
                              'world': world}
         assert dmax == 0.0, 'ranks hold different parameters after the step: max |d| = %g' % dmax
         assert train['dp_check']['grad_projection_rel_diff'] < 1e-4, train['dp_check']
+        # the same step with batch-norm statistics over the global batch (the reference's single-device semantics)
+        tr_sync = train_utils.Trainer(topts, store=nets.ParamStore(device=dev, seed=0), sync_bn=True)
+        for _ in range(2):
+            tr_sync.train_step(tbatch)
+        train['sync_bn_ms_per_step'] = max_over_ranks(timed_steps(lambda: tr_sync.train_step(tbatch), t_steps, barrier))
+        del tr_sync
+        nets.set_sync_bn(False)
     del trainer
     nets.set_conv_mode(head_mode)
 

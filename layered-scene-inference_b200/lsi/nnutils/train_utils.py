@@ -9,8 +9,10 @@ arithmetic, the hyper-parameters and the checkpoint save / resume / pretrain-res
   * seed 0                                                                                   train_utils.py:158-160
 
 Data parallelism (not in the reference): one process per GPU, each rank runs the step on its shard of the
-batch (batch-norm statistics are per replica), then ONE all-reduce (sum) of the flat gradient buffer over NCCL and a
-fused Adam step on the flat parameter buffer with the gradients scaled by 1/world_size.
+batch, then ONE all-reduce (sum) of the flat gradient buffer over NCCL and a fused Adam step on the flat parameter buffer
+with the gradients scaled by 1/world_size.  Batch-norm statistics are per replica by default; Trainer(sync_bn=True)
+all-reduces the per-channel sums of every BN layer (forward and backward) so that the N-rank step equals the reference's
+single-device step on the global batch (tests/test_gpu_dp.py).
 """
 import os
 import types
@@ -180,8 +182,12 @@ class HostViewPipeline(object):
 class Trainer(object):
     """One training step of ldi_enc_dec.py on the B200 path."""
 
-    def __init__(self, opts, store=None, group=None):
+    def __init__(self, opts, store=None, group=None, sync_bn=False):
+        """sync_bn: batch-norm statistics over the GLOBAL batch (all ranks of `group`), i.e. the reference's single-device
+        semantics (nets.py:263-272) under data parallelism; default False = per-replica statistics (documented choice,
+        DESIGN.md section 7)."""
         self.opts = opts
+        self.sync_bn = bool(sync_bn)
         self.store = store if store is not None else nets.ParamStore(seed=0)
         self.group = group
         self.step_count = 0          # global_step (train_utils.py:107-116)
@@ -307,6 +313,7 @@ class Trainer(object):
         """forward -> loss -> backward -> all-reduce(sum) of the flat gradients -> Adam.  Returns (total_loss, parts); with
         dp_check=True also a dict proving the collective: <sum over ranks of the shard gradients, r> against <all-reduced
         gradient, r> for a fixed random vector r (identical on every rank)."""
+        nets.set_sync_bn(self.sync_bn, self.group)
         if self.store.flat is None:
             self._build_variables(batch)
         self.store.zero_grad()
