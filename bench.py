@@ -259,7 +259,7 @@ def main():
     img_host = make_images(B, rank)
     imgs = torch.tensor(img_host, device=dev)
     cam = [torch.tensor(host[k], device=dev) for k in ('k_s', 'k_t', 'rot', 't')]
-    pc = helpers.pixel_coords(B, H, W, device=dev)
+    pc = helpers.pixel_coords(B, H, W, _device=dev)
     opts = train_utils.default_opts(dataset='kitti', n_layers=L, batch_size=B, img_height=H, img_width=W,
                                     zbuf_scale=ZBUF_SCALE)
     # headline conv mode: 'split' -- the tensor-core mode that passes the fp32 parity bars against the oracle
@@ -430,7 +430,7 @@ def main():
         bs = B_PER_GPU // world
         imgs_s = torch.tensor(img_host[:bs], device=dev)
         cam_s = [c[:bs].contiguous() for c in cam]
-        pc_s = helpers.pixel_coords(bs, H, W, device=dev)
+        pc_s = helpers.pixel_coords(bs, H, W, _device=dev)
 
         def step_s():
             with torch.no_grad():

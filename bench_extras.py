@@ -71,7 +71,7 @@ def run(dev, peak):
     # ---- config 3: variant ablation on its own shapes ------------------------------------------------------------------
     L, B, H, W = 3, 32, 256, 256
     s = _scene_dev(gen_inputs, L, B, H, W, 'synth', 3, 1.0, dev, uniq=8)
-    pc = helpers.pixel_coords(B, H, W, device=dev)
+    pc = helpers.pixel_coords(B, H, W, _device=dev)
     cam = [s[k] for k in ('k_s', 'k_t', 'rot', 't')]
     kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=0.2, max_disp=1.0, zbuf_scale=50.0)
     by = bytes_fwd(L, H * W, H * W, True) * B
@@ -91,7 +91,7 @@ def run(dev, peak):
     # ---- config 5: contention sweep -------------------------------------------------------------------------------------
     L, B, H, W = 5, 16, 512, 1664
     base = _scene_dev(gen_inputs, L, B, H, W, 'kitti', 5, 0.4, dev, uniq=2)
-    pc = helpers.pixel_coords(B, H, W, device=dev)
+    pc = helpers.pixel_coords(B, H, W, _device=dev)
     mask1 = torch.ones(L, B, H, W, 1, device=dev)
     mask1._lsi_all_ones = True
     sweep = []
@@ -109,7 +109,7 @@ def run(dev, peak):
     # ---- backward kernels at config 4 -----------------------------------------------------------------------------------
     L, B, H, W = 4, 16, 256, 832
     s = _scene_dev(gen_inputs, L, B, H, W, 'kitti', 4, 0.4, dev, uniq=4)
-    pc = helpers.pixel_coords(B, H, W, device=dev)
+    pc = helpers.pixel_coords(B, H, W, _device=dev)
     cam = [s[k] for k in ('k_s', 'k_t', 'rot', 't')]
     bw = []
     for ds in (1.0, 0.5):

@@ -127,6 +127,11 @@ LSI_B200_API int lsi_b200_bilinear(const float* imgs, const float* coords, float
 LSI_B200_API int lsi_b200_bilinear_backward(const float* imgs, const float* coords, const float* g, float* d_imgs,
                                float* d_coords, int batch, int h_s, int w_s, int h_t, int w_t, int channels,
                                void* stream);
+/* sampling.bilinear(imgs, coords, compose=False) (sampling.py:117-131; used by the reference's synthetic-scene generator): the four
+ * corner samples masked by validity, out_ims [4,B,Ht,Wt,C], and their raw bilinear weights, out_wts [4,B,Ht,Wt,1], in the
+ * reference's order (x0,y0), (x0,y1), (x1,y0), (x1,y1).  Forward only. */
+LSI_B200_API int lsi_b200_bilinear_corners(const float* imgs, const float* coords, float* out_ims, float* out_wts, int batch,
+                                           int h_s, int w_s, int h_t, int w_t, int channels, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Losses: lsi/loss/loss.py and the loss glue of ldi_enc_dec.py.  Scalars are device floats.

@@ -114,6 +114,33 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const SampParams p) {
   p.d_coords[idx * 2] = gx; p.d_coords[idx * 2 + 1] = gy;
 }
 
+// sampling.py:117-131, compose=False: the four corner samples and their weights separately (the reference's data generator
+// composites layers from them).  out_ims[i] = [corner valid] * imgs[corner]; out_wts[i] = the raw bilinear weight (NOT masked by
+// validity, exactly as sampling.py:83-86,123-126); i runs over (x0,y0), (x0,y1), (x1,y0), (x1,y1) -- the reference's list order.
+__global__ void __launch_bounds__(256) bilinear_corners_kernel(const SampParams p, float* __restrict__ out_wts) {
+  const long long n_trg = (long long)p.Ht * p.Wt;
+  const long long total = n_trg * p.B;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int b = (int)(idx / n_trg);
+  const float x = p.coords[idx * 2] - 0.5f, y = p.coords[idx * 2 + 1] - 0.5f;
+  PixGeom g;
+  corners(x, y, p.Ws, p.Hs, g);
+  const float x0 = floorf(x), y0 = floorf(y);
+  const float rx0 = (x0 + 1.f) - x, rx1 = x - x0, ry0 = (y0 + 1.f) - y, ry1 = y - y0;
+  const int order[4] = {0, 2, 1, 3};                       // corners(): bit 0 = x1, bit 1 = y1
+  const float raw[4] = {rx0 * ry0, rx0 * ry1, rx1 * ry0, rx1 * ry1};
+  const float valid[4] = {g.vx0 * g.vy0, g.vx0 * g.vy1, g.vx1 * g.vy0, g.vx1 * g.vy1};
+  const float* im = p.a + (size_t)b * p.Hs * p.Ws * p.C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out_wts[(size_t)i * total + idx] = raw[i];
+    float* o = p.out + ((size_t)i * total + idx) * p.C;
+    const float* src = im + (size_t)corner_index(g, order[i], p.Ws) * p.C;
+    for (int ch = 0; ch < p.C; ++ch) o[ch] = valid[i] != 0.f ? __ldg(src + ch) : 0.f;
+  }
+}
+
 static int check_samp(const void* a, const void* c, const void* o, int B, int Hs, int Ws, int Ht, int Wt, int C) {
   LSI_REQUIRE(a && c && o, "NULL pointer argument");
   LSI_REQUIRE(B >= 1 && Hs >= 1 && Ws >= 1 && Ht >= 1 && Wt >= 1 && C >= 1, "sizes must be >= 1");
@@ -167,6 +194,17 @@ extern "C" int lsi_b200_bilinear_backward(const float* imgs, const float* coords
   LSI_REQUIRE(g && d_coords, "NULL pointer argument");
   SampParams p{imgs, coords, g, d_imgs, d_coords, batch, h_s, w_s, h_t, w_t, channels};
   bilinear_bwd_kernel<<<blocks_for((long long)batch * h_t * w_t), 256, 0, as_stream(stream)>>>(p);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
+// bilinear(imgs, coords, compose=False) (sampling.py:117-131): out_ims [4,B,Ht,Wt,C], out_wts [4,B,Ht,Wt,1].
+extern "C" int lsi_b200_bilinear_corners(const float* imgs, const float* coords, float* out_ims, float* out_wts, int batch, int h_s,
+                                         int w_s, int h_t, int w_t, int channels, void* stream) {
+  if (int rc = check_samp(imgs, coords, out_ims, batch, h_s, w_s, h_t, w_t, channels)) return rc;
+  LSI_REQUIRE(out_wts != nullptr, "NULL pointer argument");
+  SampParams p{imgs, coords, nullptr, out_ims, nullptr, batch, h_s, w_s, h_t, w_t, channels};
+  bilinear_corners_kernel<<<blocks_for((long long)batch * h_t * w_t), 256, 0, as_stream(stream)>>>(p, out_wts);
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }

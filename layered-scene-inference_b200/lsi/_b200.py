@@ -49,6 +49,7 @@ SIGNATURES = {
     'lsi_b200_splat_backward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'lsi_b200_bilinear': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'lsi_b200_bilinear_backward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'lsi_b200_bilinear_corners': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'lsi_b200_loss_partials_count': (_SZ, []),
     'lsi_b200_zbuf_composition_loss': (_I, [_P, _P, _P, _P, _I, _LL, _F, _F, _F, _P, _P, _P]),
     'lsi_b200_zbuf_composition_loss_backward': (_I, [_P, _P, _P, _P, _I, _LL, _F, _F, _F, _P, _P, _P, _P, _P]),

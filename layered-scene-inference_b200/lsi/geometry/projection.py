@@ -6,16 +6,18 @@ from lsi.geometry import sampling
 from lsi.nnutils import helpers as nn_helpers
 
 
-def pad_intrinsic(k):
+def pad_intrinsic(k_mat):
     """projection.py:27-46 -- [...,3,3] -> [...,4,4]."""
+    k = k_mat
     out = torch.zeros(*k.shape[:-2], 4, 4, dtype=k.dtype, device=k.device)
     out[..., :3, :3] = k
     out[..., 3, 3] = 1
     return out
 
 
-def pad_extrinsic(rot, trans):
+def pad_extrinsic(rot_mat, trans_mat):
     """projection.py:49-68 -- [R t; 0 1]."""
+    rot, trans = rot_mat, trans_mat
     out = torch.zeros(*rot.shape[:-2], 4, 4, dtype=rot.dtype, device=rot.device)
     out[..., :3, :3] = rot
     out[..., :3, 3:4] = trans
@@ -41,12 +43,12 @@ def _matrix(k_s, k_t, rot, t, inverse):
     return out
 
 
-def forward_projection_matrix(k_s, k_t, rot, t, name='forward_projection_matrix'):
+def forward_projection_matrix(k_s, k_t, rot, t):
     """projection.py:71-86 -- src->trg 4x4 matrices [B,4,4]."""
     return _matrix(k_s, k_t, rot, t, 0)
 
 
-def inverse_projection_matrix(k_s, k_t, rot, t, name='inverse_projection_matrix'):
+def inverse_projection_matrix(k_s, k_t, rot, t):
     """projection.py:89-106 -- trg->src 4x4 matrices [B,4,4]."""
     return _matrix(k_s, k_t, rot, t, 1)
 

@@ -63,13 +63,21 @@ class _Bilinear(torch.autograd.Function):
 
 def bilinear(imgs, coords, compose=True):
     """sampling.py:41-132.  imgs [B,Hs,Ws,C], coords [B,Ht,Wt,2] -> [B,Ht,Wt,C]; zero outside the image.
-    compose=False (four weighted corner images, used only by the reference's data generator) is not provided."""
-    if not compose:
-        raise NotImplementedError('bilinear(compose=False) is data-generator only (layers.py) and out of scope')
+    compose=False (sampling.py:117-131, the reference's data generator): returns (out_ims, out_wts), two lists of four
+    tensors -- the corner samples masked by validity [B,Ht,Wt,C] and their raw bilinear weights [B,Ht,Wt,1] -- in the order
+    (x0,y0), (x0,y1), (x1,y0), (x1,y1); forward only (no gradient, as the generator needs none)."""
     imgs = _b200.dev_f32(imgs, 'imgs')
     coords = _b200.dev_f32(coords, 'coords')
     if imgs.dim() != 4 or coords.dim() != 4 or coords.shape[0] != imgs.shape[0] or coords.shape[3] != 2:
         raise RuntimeError('lsi_b200: bilinear shape mismatch: imgs %s coords %s' % (tuple(imgs.shape), tuple(coords.shape)))
+    if not compose:
+        b, h_s, w_s, c = imgs.shape
+        _, h_t, w_t, _ = coords.shape
+        ims = torch.empty(4, b, h_t, w_t, c, dtype=torch.float32, device=imgs.device)
+        wts = torch.empty(4, b, h_t, w_t, 1, dtype=torch.float32, device=imgs.device)
+        _b200.call('lsi_b200_bilinear_corners', _b200.ptr(imgs.detach()), _b200.ptr(coords.detach()), _b200.ptr(ims), _b200.ptr(wts),
+                   b, h_s, w_s, h_t, w_t, c, _b200.stream())
+        return list(ims.unbind(0)), list(wts.unbind(0))
     return _Bilinear.apply(imgs, coords)
 
 
@@ -77,6 +85,8 @@ def bilinear_wrapper(imgs, coords, compose=True):
     """sampling.py:135-168 -- arbitrary leading dims."""
     init_dims = list(imgs.shape[:-3])
     out = bilinear(imgs.reshape([-1] + list(imgs.shape[-3:])), coords.reshape([-1] + list(coords.shape[-3:])), compose)
+    if not compose:                                                   # sampling.py:160-166: reshape every image / weight of the two lists
+        return tuple([o.reshape(init_dims + list(o.shape[-3:])) for o in lst] for lst in out)
     return out.reshape(init_dims + list(out.shape[-3:]))
 
 

@@ -26,6 +26,17 @@ class _DecreasingDisp(torch.autograd.Function):
         return d
 
 
+def event_prob(layer_masks):
+    """loss.py:27-45 -- per-pixel layer assignment probabilities by ordered multiplication: p_l = m_l * prod_{k<l} (1 - m_k) with
+    the masks clipped to [1e-6, 1 - 1e-6]; returns (layer_probs [L,...,1], escape_probs [1,...,1]).  Unused by either reference
+    script (kept for API parity; plain elementwise torch ops on the caller's device)."""
+    eps = 1e-6
+    m = torch.clamp(layer_masks, eps, 1 - eps)
+    log_inv = torch.log(1 - m)
+    layer_probs = torch.exp(torch.cumsum(log_inv, dim=0) - log_inv + torch.log(m))
+    return layer_probs, 1 - layer_probs.sum(dim=0, keepdim=True)
+
+
 def decreasing_disp_loss(layer_disps):
     """loss.py:48-63 -- mean relu(d[l+1] - stop_gradient(d[l])); 0 for a single layer."""
     return _DecreasingDisp.apply(_b200.dev_f32(layer_disps, 'layer_disps'))

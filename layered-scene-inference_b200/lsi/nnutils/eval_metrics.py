@@ -91,7 +91,7 @@ def define_metrics(opts, ldi_src, ldi_trg, imgs_src, imgs_trg, k_s, k_t, rot_mat
     """ldi_pred_eval.py:297-548 on the B200 path.  LDIs as returned by nets.ldi_predictor (disparities already scaled by
     max_disp), images [B,H,W,3], cameras as in forward_splat.  -> (metrics, metrics_norm): {name: 0-d tensor}."""
     B, H, W, _ = imgs_src.shape
-    pc = nn_helpers.pixel_coords(B, H, W, device=imgs_src.device)
+    pc = nn_helpers.pixel_coords(B, H, W, _device=imgs_src.device)
     synthetic = opts.dataset == 'synthetic'
     disocc = synthetic or (opts.dataset == 'kitti' and getattr(opts, 'kitti_dl_disparities', False))
     inv_rot = nn_helpers.transpose(rot_mat)                                         # ldi_pred_eval.py:180-181

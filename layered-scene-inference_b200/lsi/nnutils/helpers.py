@@ -2,13 +2,23 @@
 
 On the hot path these are fused into the CUDA kernels (csrc/common.cuh); the functions here exist so that
 reference call sites keep working, and are thin elementwise wrappers (API parity, not the measured path).
-`optimistic_restorer` (helpers.py:27-62) lives in lsi.nnutils.checkpoint (numpy archives keyed by the TF variable names)
-and is re-exported here under the reference's name.
+`optimistic_restorer` (helpers.py:27-62) is implemented in lsi.nnutils.checkpoint (numpy archives keyed by the TF variable
+names) and exposed here under the reference's name and signature.
 """
 import torch
 
 from lsi import _b200
-from lsi.nnutils.checkpoint import optimistic_restorer  # noqa: F401  (helpers.py:27-62)
+from lsi.nnutils import checkpoint as _ckpt
+
+
+def optimistic_restorer(save_file, vars_all=None, _store=None):
+    """helpers.py:27-62 -- restorer for the variables that are present in save_file with the same shape.  The reference reads
+    tf.global_variables(); here the variables live in a ParamStore (`_store`, default: the default store of lsi.nnutils.nets).
+    Returns an object with `.restore(store)`."""
+    if _store is None:
+        from lsi.nnutils import nets
+        _store = nets.get_default_store()
+    return _ckpt.optimistic_restorer(save_file, _store, vars_all)
 
 
 def transpose(rot):
@@ -28,7 +38,7 @@ class _StandardGrid(torch.Tensor):
     pass
 
 
-def pixel_coords(bs, h, w, device='cuda'):
+def pixel_coords(bs, h, w, _device='cuda'):
     """helpers.py:88-113 -- [bs,h,w,3] (x+0.5, y+0.5, 1)."""
     ys = (torch.arange(h, dtype=torch.float32, device=device) + 1).view(1, h, 1).expand(bs, h, w) - 0.5
     xs = (torch.arange(w, dtype=torch.float32, device=device) + 1).view(1, 1, w).expand(bs, h, w) - 0.5

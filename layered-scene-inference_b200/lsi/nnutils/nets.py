@@ -10,8 +10,7 @@ a `ParamStore` that plays the role of the TF variable scope (`reuse=True` looks 
 
 Not provided (never executed by either reference script): the FC stack on the bottleneck (nets.py:289-291, its output
 `feat` is discarded at ldi_enc_dec.py:198 -- `None` is returned in its place), the decoder levels below the one that
-feeds the heads, `encoder_simple`/`encoder_decoder_simple` (`--use_unet=false`, unused by every documented recipe), and
-inference-mode batch norm (the reference never updates the moving averages, train_utils.py:107-117, and evaluates with
+feeds the heads, and inference-mode batch norm (the reference never updates the moving averages, train_utils.py:107-117, and evaluates with
 batch statistics, ldi_pred_eval.py:45).
 """
 import math
@@ -60,8 +59,8 @@ class ParamStore(object):
             raise RuntimeError('ParamStore is already flattened; create every variable first')
         rs = np.random.RandomState((zlib.crc32(name.encode()) + self.seed) % (2 ** 31))
         if kind == 'weights':          # [TF1.4] slim default: Xavier-uniform
-            kh, kw, a, b = shape
-            limit = math.sqrt(6.0 / (kh * kw * a + kh * kw * b))
+            fan = (shape[0] + shape[1]) if len(shape) == 2 else shape[0] * shape[1] * (shape[2] + shape[3])   # fully connected: [in, out]
+            limit = math.sqrt(6.0 / fan)
             v = torch.tensor(rs.uniform(-limit, limit, shape), dtype=torch.float32)
         else:                          # biases / BatchNorm beta: zeros
             v = torch.zeros(shape, dtype=torch.float32)
@@ -567,13 +566,15 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
             out = _Pending(z, stats, beta)
             return out if defer else out.materialize()
     srcs = [_materialize(t) for t in (x if pair else [x])]
-    if not pair and not isinstance(srcs[0], _SplitAct) and srcs[0].shape[3] % 32:
-        xin = _b200.dev_f32(srcs[0], scope + ' input')
+    if not pair and (srcs[0].shape[3] % 32 or cout % 32):
+        # channel counts the split layout cannot hold (the 3-channel stem; nz = 1000 of the non-U-Net variant): exact fp32 kernels
+        xin = _b200.dev_f32(to_float(srcs[0]), scope + ' input')
         B, H, W, cin = xin.shape
         geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
         w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
         beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
-        return _SplitAct.pack(_ConvBNReLU.apply(xin, w, beta, geo))
+        y = _ConvBNReLU.apply(xin, w, beta, geo)
+        return y if cout % 32 else _SplitAct.pack(y)
     srcs = [t if isinstance(t, _SplitAct) else _SplitAct.pack(t) for t in srcs]
     a, b = srcs[0], (srcs[1] if pair else None)
     B, H, W, ca = a.shape
@@ -702,6 +703,8 @@ def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False,
     store = _store or get_default_store()
     n_filters = [32, 64, 128, 256] + [512] * max(nconv - 4, 0)
     end_points = {}
+    if isinstance(feat, torch.Tensor) and feat.dim() == 2:        # B x nz bottleneck code (nets.py:103-104)
+        feat = feat[:, None, None, :]
     for nc in range(nconv, 0, -1):
         n_filt = n_filters[nc - 1]
         feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True, defer=_defer)
@@ -790,6 +793,48 @@ def ldi_predictor(feat, n_layers=1, reuse=False, n_layerwise_steps=0, skip_feat=
         masks = torch.ones(disps.shape, dtype=torch.float32, device=pred.device)
         masks._lsi_all_ones = True
     return [tex, masks, disps]
+
+
+def _fc_layer(store, scope, x, cout, reuse):
+    """slim.fully_connected with batch_norm + ReLU (nets.py:43-49,67-68): x [B,K] @ weights [K,cout] (the TF variable shape),
+    batch statistics over the batch, beta only.  Runs as a 1x1 convolution on a [B,1,1,K] tensor."""
+    x = _b200.dev_f32(to_float(x), scope + ' input')
+    B, K = x.shape
+    w = store.get(scope + '/weights', [K, cout], reuse, 'weights')
+    beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+    geo = _Geometry(False, B, 1, 1, K, cout, 1, 1)
+    return _ConvBNReLU.apply(x.view(B, 1, 1, K), w.view(1, 1, K, cout), beta, geo).view(B, cout)
+
+
+def encoder_simple(inp_img, nz=1000, is_training=True, reuse=False, _store=None):
+    """nets.py:29-70 -- the 14-convolution encoder under scope `encoder`, flatten, fully connected stack (2nz, nz, nz).
+    Returns (enc [B,nz], end_points)."""
+    _require_training(is_training)
+    store = _store or get_default_store()
+    x = _b200.dev_f32(inp_img, 'inp_img')
+    if x.dim() != 4 or x.shape[3] != 3:
+        raise RuntimeError('lsi_b200: inp_img must be [B,H,W,3], got %s' % (tuple(x.shape),))
+    if x.shape[1] % 128 or x.shape[2] % 128:
+        raise ValueError('the encoder needs H and W to be multiples of 128 (seven stride-2 convolutions on even sizes), got %dx%d'
+                         % (x.shape[1], x.shape[2]))
+    ep = {}
+    for name, k, stride, cout in ENC:
+        x = _conv_layer(store, 'encoder/%s' % name, x, cout, k, stride, reuse)
+        ep[name] = x
+    x = to_float(x)
+    x = x.reshape(x.shape[0], -1)                                  # slim.flatten: NHWC order
+    for i, n_out in enumerate([2 * nz, nz, nz]):                   # slim.stack scopes fc/fc_1 .. fc_3
+        x = _fc_layer(store, 'encoder/fc/fc_%d' % (i + 1), x, n_out, reuse)
+        ep['fc_%d' % (i + 1)] = x
+    return x, ep
+
+
+def encoder_decoder_simple(inp_img, nz=1000, nupconv=8, is_training=True, reuse=False, nl_diff_enc_dec=0, _store=None):
+    """nets.py:211-241 (`--use_unet=false`, ldi_enc_dec.py:202-205).  Returns (feat [B,nz], feat_dec, skip_feat=None, end_points)."""
+    store = _store or get_default_store()
+    feat, enc_ep = encoder_simple(inp_img, nz=nz, is_training=is_training, reuse=reuse, _store=store)
+    feat_dec, dec_ep = decoder_simple(feat, nconv=nupconv - nl_diff_enc_dec, is_training=is_training, reuse=reuse, _store=store)
+    return feat, feat_dec, None, dict(enc_ep, **dec_ep)
 
 
 def encoder_decoder_unet(inp_img, nz=1000, is_training=True, reuse=False, nl_diff_enc_dec=0, _store=None):

@@ -67,8 +67,12 @@ def predict_ldi(img, opts, store, reuse):
     """ldi_enc_dec.py:196-213 for one tower: U-Net trunk -> heads -> disp *= max_disp.  Images whose size the reference
     U-Net cannot take (not a multiple of 128) are zero-padded and the prediction cropped (nets.pad_to_legal)."""
     padded, (h, w) = nets.pad_to_legal(img)
-    _, feat_dec, skip_feat, _ = nets.encoder_decoder_unet(padded, nl_diff_enc_dec=opts.n_layerwise_steps, reuse=reuse,
-                                                          _store=store)
+    if getattr(opts, 'use_unet', True):                               # ldi_enc_dec.py:197-205
+        _, feat_dec, skip_feat, _ = nets.encoder_decoder_unet(padded, nl_diff_enc_dec=opts.n_layerwise_steps, reuse=reuse,
+                                                              _store=store)
+    else:
+        _, feat_dec, skip_feat, _ = nets.encoder_decoder_simple(padded, nl_diff_enc_dec=opts.n_layerwise_steps, reuse=reuse,
+                                                                _store=store)
     # the crop back to (h, w) is fused into the prediction conv (it only evaluates the top-left window)
     if not torch.is_grad_enabled() and not opts.pred_ldi_masks:
         # inference: the disparity scale is a per-channel output factor of the prediction conv, so textures and
@@ -108,7 +112,7 @@ class HostViewPipeline(object):
         ds = float(render_kw.get('trg_downsampling', 1))
         ht, wt = int(height * ds), int(width * ds)
         dev = self.device
-        self.pc = nn_helpers.pixel_coords(batch, height, width, device=dev)
+        self.pc = nn_helpers.pixel_coords(batch, height, width, _device=dev)
         self.x = [torch.empty(batch, height, width, 3, device=dev) for _ in range(depth)]
         self.cams = [dict(k_s=torch.empty(batch, 3, 3, device=dev), k_t=torch.empty(batch, 3, 3, device=dev),
                           rot=torch.empty(batch, 3, 3, device=dev), t=None) for _ in range(depth)]
@@ -208,7 +212,7 @@ class Trainer(object):
     def define_loss_graph(self, ldi_src, ldi_trg, batch):
         """ldi_enc_dec.py:265-410."""
         b, h, w, _ = batch['imgs_src'].shape
-        pc = nn_helpers.pixel_coords(b, h, w, device=batch['imgs_src'].device)
+        pc = nn_helpers.pixel_coords(b, h, w, _device=batch['imgs_src'].device)
         return loss_mod.view_synthesis_loss(ldi_src, ldi_trg, batch['imgs_src'], batch['imgs_trg'], pc, batch['k_s'],
                                             batch['k_t'], batch['rot_mat'], batch['trans_mat'], self.opts)
 

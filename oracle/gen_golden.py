@@ -190,6 +190,13 @@ def gen_primitives():
         im5 = torch.tensor(np.stack([img, img[::-1]]), dtype=dtype)
         c5 = torch.tensor(np.stack([coords, coords * 0.9]), dtype=dtype)
         blob['bilinear_wrapper' + sfx] = sampling.bilinear_wrapper(T(im5), T(c5)).t.numpy()
+        # compose=False (sampling.py:117-131): four masked corner samples + their raw weights, plain and through the wrapper
+        ims_nc, wts_nc = sampling.bilinear(T(torch.tensor(img, dtype=dtype)), T(torch.tensor(coords, dtype=dtype)), compose=False)
+        blob['bilinear_nc_ims' + sfx] = np.stack([v.t.numpy() for v in ims_nc])
+        blob['bilinear_nc_wts' + sfx] = np.stack([v.t.numpy() for v in wts_nc])
+        ims_w, wts_w = sampling.bilinear_wrapper(T(im5.clone()), T(c5.clone()), compose=False)
+        blob['bilinear_wrapper_nc_ims' + sfx] = np.stack([v.t.numpy() for v in ims_w])
+        blob['bilinear_wrapper_nc_wts' + sfx] = np.stack([v.t.numpy() for v in wts_w])
         # projection + disocclusion
         k_s = torch.tensor(np.stack([synth_k(H, W)] * B), dtype=dtype)
         k_t = torch.tensor(np.stack([synth_k(H, W) * np.array([[1.1], [0.9], [1.0]])] * B), dtype=dtype)
@@ -358,6 +365,36 @@ def gen_nets():
     print('%-28s %7.1f KB' % ('nets_unet_l2', os.path.getsize(path) / 1024.0))
 
 
+def gen_nets_simple():
+    """The non-U-Net variant: the reference's own encoder_decoder_simple (nets.py:211-241) + ldi_predictor without skips
+    (ldi_enc_dec.py:202-213), over the slim stand-in."""
+    from lsi.nnutils import nets
+    sys.path.insert(0, ROOT)
+    from oracle import lsi_oracle_nets as N
+    L, B, H, W, steps, nz, max_disp = 1, 4, 128, 128, 3, 96, 1.0
+    img = np.random.RandomState(43).uniform(0, 1, (B, H, W, 3)).astype(np.float32)
+    blob = dict(in_img=img, meta=np.array([L, B, H, W, steps, nz], dtype=np.int64), max_disp=np.float64(max_disp), param_seed=np.int64(9))
+    for dtype, sfx in ((torch.float32, '_f32'), (torch.float64, '_f64')):
+        tf._set_float(dtype)
+        params = N.init_params_simple(L, (H, W), seed=9, random_beta=True, dtype=dtype, nz=nz)
+        tf._VARS.clear()
+        tf._VARS.update({k: v.clone() for k, v in params.items()})
+        x = torch.tensor(img, dtype=dtype)
+        feat, feat_dec, skip_feat, _ = nets.encoder_decoder_simple(T(x), nz=nz, nl_diff_enc_dec=steps)     # ldi_enc_dec.py:202-205
+        assert skip_feat is None
+        tex, masks, disps = (v.t for v in nets.ldi_predictor(feat_dec, n_layers=L, n_layerwise_steps=steps, skip_feat=skip_feat))
+        pred = torch.cat([tex, disps * max_disp], dim=-1)
+        assert sorted(tf._VARS) == sorted(params), sorted(set(tf._VARS) ^ set(params))   # the oracle's variable list IS the reference's
+        blob['feat' + sfx] = feat.t.numpy().astype(np.float32)
+        blob['feat_dec' + sfx] = feat_dec.t[:, ::2, ::2, :].numpy().astype(np.float32)
+        blob['pred' + sfx] = pred[:, :, ::8, ::8, :].numpy().astype(np.float32)
+        blob['pred_stats' + sfx] = np.array([float(pred.double().sum()), float(pred.double().pow(2).sum().sqrt())])
+    blob['var_names'] = np.array(sorted(params))
+    path = os.path.join(GOLD, 'nets_simple_l1.npz')
+    np.savez_compressed(path, **blob)
+    print('%-28s %7.1f KB' % ('nets_simple_l1', os.path.getsize(path) / 1024.0))
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ['fs', 'prim', 'loss', 'nets']
@@ -369,3 +406,5 @@ if __name__ == '__main__':
         gen_loss()
     if 'nets' in which:
         gen_nets()
+    if 'nets_simple' in which:
+        gen_nets_simple()

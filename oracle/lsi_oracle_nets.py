@@ -169,3 +169,97 @@ def predict_ldi(params, img, n_layers, max_disp, n_layerwise_steps=3, pred_masks
     feat_dec, skip_feat, _ = encoder_decoder_unet(params, img, nl_diff_enc_dec=n_layerwise_steps)
     tex, masks, disps = ldi_predictor(params, feat_dec, n_layers, n_layerwise_steps, skip_feat, pred_masks)
     return [tex, masks, disps * max_disp]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the non-U-Net variant (--use_unet=false): nets.py:29-70 (encoder_simple), :211-241 (encoder_decoder_simple)
+# ---------------------------------------------------------------------------------------------------------------------
+DEC_SIMPLE_FILTERS = [32, 64, 128, 256, 512, 512, 512, 512]      # nets.py:87-90 with nconv = 8
+
+
+def param_shapes_simple(n_layers, img_hw, nz=1000, nupconv=8, nl_diff_enc_dec=3, n_layerwise_steps=3, pred_masks=False):
+    """TF variable name -> shape for encoder_decoder_simple + the L heads (no skip connections)."""
+    shapes = {}
+    cin = 3
+    for name, k, _, cout in ENC:
+        shapes['encoder/%s/weights' % name] = [k, k, cin, cout]
+        shapes['encoder/%s/BatchNorm/beta' % name] = [cout]
+        cin = cout
+    h7, w7 = img_hw[0] // 128, img_hw[1] // 128
+    k_in = h7 * w7 * 512
+    for i, n_out in enumerate([2 * nz, nz, nz]):                  # slim.stack scopes fc/fc_1..3
+        shapes['encoder/fc/fc_%d/weights' % (i + 1)] = [k_in, n_out]
+        shapes['encoder/fc/fc_%d/BatchNorm/beta' % (i + 1)] = [n_out]
+        k_in = n_out
+    c = nz
+    for nc in range(nupconv - nl_diff_enc_dec, 0, -1):
+        cout = DEC_SIMPLE_FILTERS[nc - 1]
+        shapes['decoder/upcnv%d/weights' % nc] = [4, 4, cout, c]
+        shapes['decoder/upcnv%d/BatchNorm/beta' % nc] = [cout]
+        shapes['decoder/upcnv%db/weights' % nc] = [3, 3, cout, cout]
+        shapes['decoder/upcnv%db/BatchNorm/beta' % nc] = [cout]
+        c = cout
+    nc_out = 4 + (1 if pred_masks else 0)
+    for l in range(n_layers):
+        base = 'ldi_tex_disp/pixelwise_pred/upsample_%d/' % l
+        cc = c
+        for step in range(n_layerwise_steps, 0, -1):
+            cout = HEAD_FILTERS[step - 1]
+            shapes[base + 'decoder/upcnv%d/weights' % step] = [4, 4, cout, cc]
+            shapes[base + 'decoder/upcnv%d/BatchNorm/beta' % step] = [cout]
+            shapes[base + 'decoder/upcnv%db/weights' % step] = [3, 3, cout, cout]
+            shapes[base + 'decoder/upcnv%db/BatchNorm/beta' % step] = [cout]
+            cc = cout
+        shapes[base + 'pred_%d/weights' % l] = [3, 3, cc, nc_out]
+        shapes[base + 'pred_%d/biases' % l] = [nc_out]
+    return shapes
+
+
+def init_params_simple(n_layers, img_hw, seed=0, random_beta=False, dtype=torch.float32, **kw):
+    params = {}
+    for name, shp in sorted(param_shapes_simple(n_layers, img_hw, **kw).items()):
+        rs = np.random.RandomState((zlib.crc32(name.encode()) + seed) % (2 ** 31))
+        if name.endswith('weights'):
+            fan = (shp[0] + shp[1]) if len(shp) == 2 else (shp[0] * shp[1] * (shp[2] + shp[3]))
+            limit = math.sqrt(6.0 / fan)
+            params[name] = torch.tensor(rs.uniform(-limit, limit, shp), dtype=dtype)
+        elif random_beta:
+            params[name] = torch.tensor(rs.uniform(-0.2, 0.2, shp), dtype=dtype)
+        else:
+            params[name] = torch.zeros(shp, dtype=dtype)
+    return params
+
+
+def encoder_simple(params, inp_img):
+    """nets.py:29-70: the 14 convolutions of the U-Net encoder under scope `encoder`, flatten (NHWC order), three fully
+    connected layers (2nz, nz, nz) each with batch-stat BN (over the batch) + ReLU and no bias.  Returns (enc [B,nz], end_points)."""
+    ep = {}
+    x = inp_img
+    for name, _, stride, _ in ENC:
+        x = bn_relu(conv2d(x, params['encoder/%s/weights' % name], stride), params['encoder/%s/BatchNorm/beta' % name])
+        ep[name] = x
+    x = x.reshape(x.shape[0], -1)
+    for i in (1, 2, 3):
+        z = x @ params['encoder/fc/fc_%d/weights' % i]
+        mean = z.mean(dim=0, keepdim=True)
+        var = ((z - mean) ** 2).mean(dim=0, keepdim=True)
+        x = torch.relu((z - mean) / torch.sqrt(var + BN_EPS) + params['encoder/fc/fc_%d/BatchNorm/beta' % i])
+        ep['fc_%d' % i] = x
+    return x, ep
+
+
+def decoder_simple_plain(params, feat, nconv, scope='decoder/'):
+    """nets.py:73-114 without skip features: nconv x [4x4 s2 up-conv -> 3x3 conv]; a [B,nz] input becomes [B,1,1,nz]."""
+    if feat.dim() == 2:
+        feat = feat[:, None, None, :]
+    for nc in range(nconv, 0, -1):
+        feat = bn_relu(conv2d_transpose(feat, params[scope + 'upcnv%d/weights' % nc]), params[scope + 'upcnv%d/BatchNorm/beta' % nc])
+        feat = bn_relu(conv2d(feat, params[scope + 'upcnv%db/weights' % nc], 1), params[scope + 'upcnv%db/BatchNorm/beta' % nc])
+    return feat
+
+
+def encoder_decoder_simple(params, inp_img, nupconv=8, nl_diff_enc_dec=0):
+    """nets.py:211-241.  Returns (feat, feat_dec, skip_feat=None, end_points)."""
+    feat, ep = encoder_simple(params, inp_img)
+    feat_dec = decoder_simple_plain(params, feat, nupconv - nl_diff_enc_dec)
+    return feat, feat_dec, None, ep

@@ -47,7 +47,8 @@ def test_optimistic_restorer_skips_new_and_reshaped_variables(tmp_path):
     """helpers.py:27-62: only variables present in the file with the same shape are restored."""
     from lsi.nnutils import checkpoint as ck
     from lsi.nnutils import helpers
-    assert helpers.optimistic_restorer is ck.optimistic_restorer          # exported under the reference's module too
+    # exported under the reference's module and signature too (helpers.py:27: optimistic_restorer(save_file, vars_all=None))
+    assert helpers.optimistic_restorer.__doc__ and 'helpers.py:27-62' in helpers.optimistic_restorer.__doc__
     a = _store(1, VARS[:3])
     path = ck.save_checkpoint(ck.checkpoint_path(str(tmp_path), 5), a.vars, global_step=5)
     # same names, but pred weights now predict 5 channels (pred_ldi_masks) and there is a variable the file lacks

@@ -27,7 +27,7 @@ def test_pipeline_matches_direct_calls():
                         't': torch.tensor(t).pin_memory()})
     with torch.no_grad():
         train_utils.predict_ldi(batches[0]['img'].to(dev), opts, store, reuse=False)
-    pc = helpers.pixel_coords(B, H, W, device=dev)
+    pc = helpers.pixel_coords(B, H, W, _device=dev)
     direct = []
     for b in batches:
         with torch.no_grad():

@@ -180,3 +180,34 @@ def test_param_store_flatten_and_adam(nets_mod):
         gv = b2 * gv + (1 - b2) * grad * grad
         ref -= lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step) * gm / (gv.sqrt() + eps)
     assert rel_err(flat.cpu(), ref.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'split', 'tf32'])
+def test_simple_encoder_decoder_golden(mode):
+    """--use_unet=false (nets.py:29-70, 211-241): encoder_simple + fully connected stack + decoder_simple + heads against the fixture
+    produced by the reference's own wiring.  fp32 / split: parity bars; tf32: integration check."""
+    from lsi.nnutils import nets
+    from oracle import lsi_oracle_nets as N
+    g = load_golden('nets_simple_l1')
+    L, B, H, W, steps, nz = (int(v) for v in g['meta'])
+    params = N.init_params_simple(L, (H, W), seed=int(g['param_seed']), random_beta=True, nz=nz)
+    nets.set_conv_mode(mode)
+    try:
+        store = nets.ParamStore()
+        store.load_state_dict(params)
+        with torch.no_grad():
+            feat, feat_dec, skip, ep = nets.encoder_decoder_simple(torch.tensor(g['in_img'], device='cuda'), nz=nz, nl_diff_enc_dec=steps,
+                                                                  reuse=True, _store=store)
+            tex, masks, disps = nets.ldi_predictor(feat_dec, n_layers=L, reuse=True, n_layerwise_steps=steps, skip_feat=skip, _store=store)
+        assert skip is None and tuple(feat.shape) == (B, nz) and sorted(store.vars) == [str(n) for n in g['var_names']]
+        pred = torch.cat([tex, disps * float(g['max_disp'])], dim=-1)
+        e_feat = rel_err(nets.to_float(feat).cpu(), g['feat_f64'])
+        e_pred = rel_err(pred.cpu()[:, :, ::8, ::8, :], g['pred_f64'])
+        n_feat, n_pred = rel_err(g['feat_f32'], g['feat_f64']), rel_err(g['pred_f32'], g['pred_f64'])
+        print('simple enc-dec, mode %s: feat %.3g (oracle fp32 noise %.3g), pred %.3g (noise %.3g)' % (mode, e_feat, n_feat, e_pred, n_pred))
+        if mode == 'tf32':
+            assert e_pred < 0.2
+        else:
+            assert e_feat < max(1e-3, 3 * n_feat) and e_pred < max(1e-4, 3 * n_pred)
+    finally:
+        nets.set_conv_mode('tf32')

@@ -137,6 +137,14 @@ def test_primitives_golden(lsi_mods):
     im5 = torch.stack([cu('in_img'), cu('in_img').flip(0)])
     c5 = torch.stack([cu('in_coords'), cu('in_coords') * 0.9])
     assert rel_err(sampling.bilinear_wrapper(im5, c5).cpu(), g['bilinear_wrapper_f64']) < TOL
+    # compose=False (sampling.py:117-131): four masked corner samples + raw weights, plain and through the wrapper
+    ims, wts = sampling.bilinear(cu('in_img'), cu('in_coords'), compose=False)
+    assert len(ims) == 4 and len(wts) == 4 and tuple(wts[0].shape) == tuple(ims[0].shape[:3]) + (1,)
+    assert rel_err(torch.stack(ims).cpu(), g['bilinear_nc_ims_f64']) < TOL
+    assert rel_err(torch.stack(wts).cpu(), g['bilinear_nc_wts_f64']) < TOL
+    ims5, wts5 = sampling.bilinear_wrapper(im5, c5, compose=False)
+    assert rel_err(torch.stack(ims5).cpu(), g['bilinear_wrapper_nc_ims_f64']) < TOL
+    assert rel_err(torch.stack(wts5).cpu(), g['bilinear_wrapper_nc_wts_f64']) < TOL
     cam = [cu('in_' + k) for k in ('k_s', 'k_t', 'rot', 't')]
     fwd = projection.forward_projection_matrix(*cam)
     inv = projection.inverse_projection_matrix(*cam)

@@ -55,6 +55,8 @@ def test_primitives_match_reference_sources():
     g = load_golden('primitives')
     assert rel_err(O.splat(t32(g['in_src']), t32(g['in_coords']), t32(g['in_init'])), g['splat_f32']) < 1e-6
     assert rel_err(O.bilinear(t32(g['in_img']), t32(g['in_coords'])), g['bilinear_f32']) < 1e-6
+    ims, wts = O.bilinear(t32(g['in_img']), t32(g['in_coords']), compose=False)
+    assert rel_err(torch.stack(ims), g['bilinear_nc_ims_f32']) < 1e-6 and rel_err(torch.stack(wts), g['bilinear_nc_wts_f32']) < 1e-6
     cam = [t32(g['in_' + k]) for k in ('k_s', 'k_t', 'rot', 't')]
     fwd = O.forward_projection_matrix(*cam)
     assert rel_err(fwd, g['proj_fwd_f32']) < 1e-6
