@@ -9,6 +9,7 @@ order is a seeded permutation (the TF queue shuffles cannot be reproduced outsid
 """
 import fnmatch
 import os
+import re
 
 import numpy as np
 import torch
@@ -17,11 +18,8 @@ from lsi import _b200
 
 
 def resize_instrinsic(intrinsic, scale_x, scale_y):
-    """data.py:32-36 (name as in the reference)."""
-    intrinsic_rsz = np.copy(intrinsic)
-    intrinsic_rsz[0, :] *= scale_x
-    intrinsic_rsz[1, :] *= scale_y
-    return intrinsic_rsz
+    """data.py:32-36 (name as in the reference): intrinsics of an image resized by (scale_x, scale_y) = diag(sx, sy, 1) @ K."""
+    return np.diag([float(scale_x), float(scale_y), 1.0]) @ np.asarray(intrinsic, dtype=np.float64)
 
 
 def raw_city_sequences():
@@ -31,42 +29,44 @@ def raw_city_sequences():
                                                              '2011_09_29_drive_0026', '2011_09_29_drive_0071'])
 
 
+_NUMERIC_LINE = re.compile(r'^[0-9eE.+\- ]+$')
+
+
 def read_calib_file(file_path):
-    """data.py:227-245 -- 'key: v0 v1 ...' lines; numeric values become float arrays, everything else stays a string."""
-    float_chars = set('0123456789.e+- ')
-    data = {}
-    with open(file_path, 'r') as f:
-        for line in f:
-            if ':' not in line:
-                continue
-            key, value = line.split(':', 1)
-            value = value.strip()
-            data[key] = value
-            if float_chars.issuperset(value):
-                try:
-                    data[key] = np.array([float(v) for v in value.split(' ')])
-                except ValueError:
-                    pass
-    return data
+    """data.py:227-245 -- a KITTI calibration file as {key: value}: `key: v0 v1 ...` lines whose value is purely numeric become
+    float64 arrays, anything else (e.g. `calib_time: 09-Jan-2012 13:57:47`) stays the stripped string."""
+    entries = {}
+    for line in open(file_path).read().splitlines():
+        key, sep, text = line.partition(':')
+        if not sep:
+            continue
+        text = text.strip()
+        entries[key] = text
+        if text and _NUMERIC_LINE.match(text):
+            try:
+                entries[key] = np.array(text.split(' '), dtype=np.float64)
+            except ValueError:
+                pass                                         # dates such as 09-01 2012 pass the character test but are not numbers
+    return entries
+
+
+def _camera_from_projection(p_rect):
+    """P_rect = K [I | c] with the offset given in homogeneous image coordinates: returns (K [3,3], c [3]) with the camera
+    offset converted to metric 3-D, c = K^-1 P[:, 3] restricted to the pinhole form K = [[fx,0,cx],[0,fy,cy],[0,0,1]]."""
+    p = np.asarray(p_rect, dtype=np.float64).reshape(3, 4)
+    k, col = p[:, :3].copy(), p[:, 3]
+    c = np.array([(col[0] - k[0, 2] * col[2]) / k[0, 0], (col[1] - k[1, 2] * col[2]) / k[1, 1], col[2]])
+    return k, c
 
 
 def stereo_cameras(calib_data, src_shape, trg_shape, h, w):
-    """data.py:303-342 (forward_instance without the images): intrinsics of cameras 2 / 3 rescaled to the network
-    resolution, identity rotation and the rectified baseline as translation.  -> (k_s, k_t, rot, trans [3,1])."""
-    rot = np.eye(3)
-    k_s = np.copy(calib_data['P_rect_02'].reshape(3, 4)[:3, :3])
-    k_t = np.copy(calib_data['P_rect_03'].reshape(3, 4)[:3, :3])
-    trans_src = np.copy(calib_data['P_rect_02'].reshape(3, 4)[:, 3])
-    trans_trg = np.copy(calib_data['P_rect_03'].reshape(3, 4)[:, 3])
-    # the translation is in homogeneous 2D coordinates: convert to regular 3D space
-    trans_src[0] = (trans_src[0] - k_s[0, 2] * trans_src[2]) / k_s[0, 0]
-    trans_src[1] = (trans_src[1] - k_s[1, 2] * trans_src[2]) / k_s[1, 1]
-    trans_trg[0] = (trans_trg[0] - k_t[0, 2] * trans_trg[2]) / k_t[0, 0]
-    trans_trg[1] = (trans_trg[1] - k_t[1, 2] * trans_trg[2]) / k_t[1, 1]
-    trans = trans_trg - trans_src
-    k_s = resize_instrinsic(k_s, w / src_shape[1], h / src_shape[0])
-    k_t = resize_instrinsic(k_t, w / trg_shape[1], h / trg_shape[0])
-    return k_s, k_t, rot, trans.reshape(3, 1)
+    """data.py:303-342 (forward_instance without the images): the colour cameras 2 (source) and 3 (target) of the rectified rig:
+    intrinsics rescaled from the image sizes to the network resolution (h, w), identity rotation (rectified pair), translation =
+    difference of the two camera offsets.  -> (k_s, k_t, rot, trans [3,1])."""
+    (k_src, c_src), (k_trg, c_trg) = (_camera_from_projection(calib_data[key]) for key in ('P_rect_02', 'P_rect_03'))
+    k_s = resize_instrinsic(k_src, w / src_shape[1], h / src_shape[0])
+    k_t = resize_instrinsic(k_trg, w / trg_shape[1], h / trg_shape[0])
+    return k_s, k_t, np.eye(3), (c_trg - c_src).reshape(3, 1)
 
 
 def split_sequences(data_split):
@@ -195,8 +195,9 @@ class DataLoader(object):
         img = np.asarray(Image.open(path))
         if img.ndim == 2:
             img = img[:, :, None]
-        if img.dtype != np.uint8:                    # 16-bit disparity PNGs: keep the reference's /255 scaling of the raw values
-            raise RuntimeError('lsi_b200: %s is not an 8-bit image' % path)
+        if img.dtype != np.uint8:
+            # limitation: the SPS-stereo disparity PNGs of --kitti_dl_disparities are 16-bit; the resize kernel takes 8-bit data only
+            raise RuntimeError('lsi_b200: %s is not an 8-bit image (16-bit disparity PNGs are not supported)' % path)
         return area_resize(img, self.h, self.w, nc), img.shape
 
     def forward(self, bs):
