@@ -40,6 +40,7 @@ class _StandardGrid(torch.Tensor):
 
 def pixel_coords(bs, h, w, _device='cuda'):
     """helpers.py:88-113 -- [bs,h,w,3] (x+0.5, y+0.5, 1)."""
+    device = _device
     ys = (torch.arange(h, dtype=torch.float32, device=device) + 1).view(1, h, 1).expand(bs, h, w) - 0.5
     xs = (torch.arange(w, dtype=torch.float32, device=device) + 1).view(1, 1, w).expand(bs, h, w) - 0.5
     out = torch.stack([xs, ys, torch.ones(bs, h, w, dtype=torch.float32, device=device)], dim=3)
