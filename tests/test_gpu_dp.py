@@ -83,7 +83,7 @@ def _worker(rank, world, port, backend, sync_bn, out, hw=H):
     opts = train_utils.default_opts(n_layers=L, batch_size=B, img_height=hw, img_width=hw)
     full = {k: torch.tensor(v, device='cuda') for k, v in _batch(11, hw, hw).items()}
     shard = train_utils.shard_batch(full, rank, world)
-    tr = train_utils.Trainer(opts, store=nets.ParamStore(device='cuda', seed=2))
+    tr = train_utils.Trainer(opts, store=nets.ParamStore(device='cuda', seed=2), sync_bn=sync_bn)
     loss, _, chk = tr.train_step(shard, dp_check=True)
     out[rank] = (tr.store.flat_grad.cpu(), tr.store.flat.cpu(), float(loss), chk)
     dist.destroy_process_group()
