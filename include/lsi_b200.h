@@ -193,6 +193,16 @@ LSI_B200_API int lsi_b200_conv2d(const lsi_b200_conv_desc* d, const float* in, c
 LSI_B200_API int lsi_b200_conv2d_wgrad(const lsi_b200_conv_desc* d, const float* big, const float* small, float* dw,
                                        void* stream);
 
+/* CUDA-core kernels for the two contractions that are too thin for the tensor-core paths and badly shaped for the generic
+ * implicit GEMM (csrc/conv_small.cu): lsi_b200_conv2d for c_in <= 8, c_out <= 32, unit stride, <= 9 taps, no epilogue (the data
+ * gradient of the prediction conv, nets.py:139-155), and lsi_b200_conv2d_wgrad for c_in <= 4, c_out == 32, <= 7x7 taps,
+ * stride 1 / 2 (the weight gradient of the stem cnv1, nets.py:273).  Same descriptor semantics as the generic entry points. */
+LSI_B200_API int lsi_b200_conv2d_thin_supported(const lsi_b200_conv_desc* d);
+LSI_B200_API int lsi_b200_conv2d_thin(const lsi_b200_conv_desc* d, const float* in, const float* w, float* out, void* stream);
+LSI_B200_API int lsi_b200_conv2d_stem_wgrad_supported(const lsi_b200_conv_desc* d);
+LSI_B200_API int lsi_b200_conv2d_stem_wgrad(const lsi_b200_conv_desc* d, const float* big, const float* small, float* dw,
+                                            void* stream);
+
 /* Tensor-core (tcgen05 + TMA, TF32 inputs / fp32 accumulate) version of lsi_b200_conv2d for layers whose summed
  * channel count is a multiple of 32, with an optional second input source that implements tf.concat on the fly:
  * channels [0, c_in_a) come from in_a (pixel stride d->in_c_stride), [c_in_a, c_in) from in_b (pixel stride
@@ -313,6 +323,10 @@ LSI_B200_API int lsi_b200_bn_relu_backward(const float* x, const float* y, const
                                            float* dbeta_sums, long long n_pixels, int channels, int x_c_stride,
                                            int y_c_stride, int dy_c_stride, int dx_c_stride, int relu, int accumulate,
                                            void* workspace, void* stream);
+/* Dense fast path of lsi_b200_bn_relu_backward for contiguous [n_pixels, channels] tensors, channels % 4 == 0, with ReLU: reads
+ * the raw conv output z and dy only (the mask is recomputed from z with the forward kernels' exact expression). */
+LSI_B200_API int lsi_b200_bn_relu_backward_z(const float* z, const float* beta, const float* dy, const float* stats, float* dx,
+                                             float* dbeta_sums, long long n_pixels, int channels, void* workspace, void* stream);
 /* lsi_b200_bn_relu_backward in two stages, for batch statistics that span several data-parallel ranks (the reference
  * normalises over the whole batch on one device, nets.py:263-272): stage 1 writes this rank's (sum dz, sum dz*xhat) to
  * dbeta_sums; the caller all-reduces them; stage 2 computes dx from the given sums with 1 / n_pixels_stat (global count). */

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
   const long long total = p.P * p.C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long q = i / p.C; const int c = (int)(i - q * p.C);
-    float v = (p.x[q * p.x_cs + c] - __ldg(p.stats + 2 * c)) * __ldg(p.stats + 2 * c + 1) + __ldg(p.beta + c);
+    float v = fmaf(p.x[q * p.x_cs + c] - __ldg(p.stats + 2 * c), __ldg(p.stats + 2 * c + 1), __ldg(p.beta + c));
     if (p.relu) v = fmaxf(v, 0.f);
     p.y[q * p.y_cs + c] = v;
   }
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(256) bn_apply_vec4_kernel(const BnApplyParams 
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.stats + 2 * c)), s1 = __ldg(reinterpret_cast<const float4*>(p.stats + 2 * c) + 1);
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
     float4 o;
-    o.x = (v.x - s0.x) * s0.y + b.x; o.y = (v.y - s0.z) * s0.w + b.y;
-    o.z = (v.z - s1.x) * s1.y + b.z; o.w = (v.w - s1.z) * s1.w + b.w;
+    o.x = fmaf(v.x - s0.x, s0.y, b.x); o.y = fmaf(v.y - s0.z, s0.w, b.y);      // explicit fma: bn_bwd_z_* recompute the ReLU mask
+    o.z = fmaf(v.z - s1.x, s1.y, b.z); o.w = fmaf(v.w - s1.z, s1.w, b.w);      // from z with exactly this expression
     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     y[i] = o;
   }
@@ -155,6 +155,87 @@ __global__ void __launch_bounds__(256) copy_channels_kernel(const float* __restr
     const long long q = i / C; const int c = (int)(i - q * C);
     const float v = src[q * src_cs + c];
     if (accumulate) dst[q * dst_cs + c] += v; else dst[q * dst_cs + c] = v;
+  }
+}
+
+// the same for 4-channel-aligned, 16-byte-aligned tensors: 128-bit accesses, 32-bit index arithmetic per row
+__global__ void __launch_bounds__(256) copy_channels_vec4_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long P,
+                                                                 int C4, int src_cs4, int dst_cs4, int accumulate) {
+  const long long total = P * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i / C4; const int c = (int)(i - q * C4);
+    float4 v = __ldcs(src + q * src_cs4 + c);
+    if (accumulate) { const float4 a = dst[q * dst_cs4 + c]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    dst[q * dst_cs4 + c] = v;
+  }
+}
+
+// Dense batch-norm + ReLU backward from the raw conv output z and the upstream gradient alone: the ReLU mask is recomputed as
+// fmaf(z - mean, rstd, beta) > 0 -- the very expression the forward kernels evaluate -- so the normalised output y is not read.
+//   stats pass   partial[blk][c] = (sum dz, sum dz * xhat) over the block's items        (2 tensor reads)
+//   apply pass   dx = rstd * (dz - sum_dz / P - xhat * sum_dzx / P)                        (2 reads, 1 write)
+// against 3 + 3 reads and 1 write of the strided general kernels.  Items are float4s of the flattened [P, C] tensors; the grid
+// stride is a multiple of C / 4, so a thread's four channels -- mean, rstd, beta and the two sums -- are loop invariants.
+struct BnBwdZParams {
+  const float4* z; const float4* dy; float4* dx;
+  const float* beta; const float* stats; const float* sums; double* partial;
+  long long total4, P; unsigned c4n; int C;
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_z_stats_kernel(const BnBwdZParams p) {
+  __shared__ float sh[256][9];
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((unsigned long long)i0 % p.c4n) * 4;
+  float mean[4], rstd[4], beta[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { mean[k] = __ldg(p.stats + 2 * (c + k)); rstd[k] = __ldg(p.stats + 2 * (c + k) + 1); beta[k] = __ldg(p.beta + c + k); }
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = i0; i < p.total4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 zv = __ldcs(p.z + i), g = __ldcs(p.dy + i);
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = zz[k] - mean[k];
+      const float dz = fmaf(d, rstd[k], beta[k]) > 0.f ? gg[k] : 0.f;
+      s[k] += dz; s[4 + k] = fmaf(dz, d * rstd[k], s[4 + k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[threadIdx.x][k] = s[k];
+  __syncthreads();
+  // thread t < c4n gathers the threads t, t + c4n, ... of this block: they all hold the same four channels
+  if (threadIdx.x < p.c4n) {
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (unsigned t = threadIdx.x; t < 256; t += p.c4n)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += (double)sh[t][k];
+    double* out = p.partial + ((size_t)blockIdx.x * p.C + c) * 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { out[2 * k] = a[k]; out[2 * k + 1] = a[4 + k]; }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_z_apply_kernel(const BnBwdZParams p) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((unsigned long long)i0 % p.c4n) * 4;
+  const float invP = 1.f / (float)p.P;
+  float mean[4], rstd[4], beta[4], m0[4], m1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mean[k] = __ldg(p.stats + 2 * (c + k)); rstd[k] = __ldg(p.stats + 2 * (c + k) + 1); beta[k] = __ldg(p.beta + c + k);
+    m0[k] = __ldg(p.sums + 2 * (c + k)) * invP; m1[k] = __ldg(p.sums + 2 * (c + k) + 1) * invP;
+  }
+  for (long long i = i0; i < p.total4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 zv = __ldcs(p.z + i), g = __ldcs(p.dy + i);
+    const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = zz[k] - mean[k];
+      const float dz = fmaf(d, rstd[k], beta[k]) > 0.f ? gg[k] : 0.f;
+      o[k] = rstd[k] * (dz - m0[k] - (d * rstd[k]) * m1[k]);
+    }
+    p.dx[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -439,6 +520,37 @@ extern "C" int lsi_b200_channel_sums(const float* x, float* sums, long long n_pi
   return LSI_B200_OK;
 }
 
+// Dense fast path of lsi_b200_bn_relu_backward (contiguous [P, C] tensors, C % 4 == 0, ReLU): reads z and dy only.
+extern "C" int lsi_b200_bn_relu_backward_z(const float* z, const float* beta, const float* dy, const float* stats, float* dx,
+                                           float* dbeta_sums, long long n_pixels, int channels, void* workspace, void* stream) {
+  LSI_REQUIRE(z && beta && dy && stats && dx && dbeta_sums && workspace, "NULL pointer argument");
+  LSI_REQUIRE(n_pixels >= 1 && channels >= 4 && channels % 4 == 0 && channels <= 1024, "channels must be a multiple of 4 (<= 1024)");
+  LSI_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0, "tensors must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  BnBwdZParams p;
+  p.z = reinterpret_cast<const float4*>(z); p.dy = reinterpret_cast<const float4*>(dy); p.dx = reinterpret_cast<float4*>(dx);
+  p.beta = beta; p.stats = stats; p.sums = dbeta_sums; p.partial = static_cast<double*>(workspace);
+  p.total4 = n_pixels * channels / 4; p.P = n_pixels; p.c4n = (unsigned)channels / 4; p.C = channels;
+  // grid: a multiple of m blocks so that gridDim.x * 256 is a multiple of c4n (threads keep their channels across iterations)
+  unsigned m = p.c4n, g256 = 256;
+  while (g256) { const unsigned t = m % g256; m = g256; g256 = t; }   // m = gcd(c4n, 256)
+  m = p.c4n / m;
+  long long want = (p.total4 + 256 * 8 - 1) / (256 * 8);
+  if (want > kStatBlocks) want = kStatBlocks;
+  unsigned nb = (unsigned)((want + m - 1) / m * m);
+  if (nb > (unsigned)kStatBlocks) nb = (unsigned)kStatBlocks / m * m;
+  LSI_REQUIRE(nb >= 1, "channel count %d not supported by the dense batch-norm backward", channels);
+  bn_bwd_z_stats_kernel<<<nb, 256, 0, st>>>(p);
+  LSI_LAUNCH_CHECK();
+  finalize_stats_kernel<<<(channels + 7) / 8, 256, 0, st>>>(static_cast<double*>(workspace), (int)nb, channels, n_pixels, 0.f, 1, dbeta_sums);
+  LSI_LAUNCH_CHECK();
+  unsigned ga = ew_grid(p.total4);
+  ga = (ga + m - 1) / m * m;
+  bn_bwd_z_apply_kernel<<<ga, 256, 0, st>>>(p);
+  LSI_LAUNCH_CHECK();
+  return LSI_B200_OK;
+}
+
 // fp64 variant: sums[c] = (sum_x, sum_x^2) as doubles -- E[x^2] - mean^2 cancels catastrophically in fp32 for channels whose mean
 // dominates their spread, so the sums that cross ranks under synchronised batch norm stay in fp64
 extern "C" int lsi_b200_channel_sums_f64(const float* x, double* sums, long long n_pixels, int channels, int x_c_stride,
@@ -460,8 +572,13 @@ extern "C" int lsi_b200_copy_channels(const float* src, float* dst, long long n_
                                       int dst_c_stride, int accumulate, void* stream) {
   LSI_REQUIRE(src && dst, "NULL pointer argument");
   LSI_REQUIRE(n_pixels >= 1 && channels >= 1 && src_c_stride >= channels && dst_c_stride >= channels, "bad sizes");
-  copy_channels_kernel<<<ew_grid(n_pixels * channels), 256, 0, as_stream(stream)>>>(src, dst, n_pixels, channels, src_c_stride,
-                                                                                     dst_c_stride, accumulate);
+  if (channels % 4 == 0 && src_c_stride % 4 == 0 && dst_c_stride % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0)
+    copy_channels_vec4_kernel<<<ew_grid(n_pixels * channels / 4), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n_pixels, channels / 4, src_c_stride / 4, dst_c_stride / 4,
+        accumulate);
+  else
+    copy_channels_kernel<<<ew_grid(n_pixels * channels), 256, 0, as_stream(stream)>>>(src, dst, n_pixels, channels, src_c_stride,
+                                                                                       dst_c_stride, accumulate);
   LSI_LAUNCH_CHECK();
   return LSI_B200_OK;
 }

@@ -263,6 +263,9 @@ def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=Non
         return False
     if inp_b is not None:
         raise RuntimeError('lsi_b200: two-source convolution needs the tensor-core path')
+    if bias is None and lib.lsi_b200_conv2d_thin_supported(d) == 1:      # e.g. the data gradient of the 32 -> 4 prediction conv
+        _b200.call('lsi_b200_conv2d_thin', d, _b200.ptr(inp), _b200.ptr(w), _b200.ptr(out), _b200.stream())
+        return False
     _b200.call('lsi_b200_conv2d', d, _b200.ptr(inp), _b200.ptr(w), _b200.ptr(bias), _b200.ptr(out), _b200.stream())
     return False
 
@@ -273,6 +276,9 @@ def _wgrad(desc_kw, big, small, dw):
             and small.data_ptr() % 16 == 0):
         _b200.call('lsi_b200_conv2d_wgrad_tc', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
         return
+    if _b200.lib().lsi_b200_conv2d_stem_wgrad_supported(d) == 1 and dw.is_contiguous():      # the 3-channel stem
+        _b200.call('lsi_b200_conv2d_stem_wgrad', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
+        return
     _b200.call('lsi_b200_conv2d_wgrad', d, _b200.ptr(big), _b200.ptr(small), _b200.ptr(dw), _b200.stream())
 
 
@@ -281,6 +287,7 @@ _HALO_F16_STORE = os.environ.get('LSI_B200_HALO_F16_STORE', '1') != '0'
 _STEM_TC = os.environ.get('LSI_B200_STEM_TC', '1') != '0'
 _HALO_CONCAT = os.environ.get('LSI_B200_HALO_CONCAT', '1') != '0'
 _OUT_SCALE_CACHE = {}
+_BN_BWD_FAST = os.environ.get('LSI_B200_BN_BWD_FAST', '1') != '0'
 _SPLIT_UPCONV_MATERIALIZE = os.environ.get('LSI_B200_SPLIT_UPCONV_MATERIALIZE', '1') != '0'
 
 
@@ -436,13 +443,13 @@ class _ConvBNReLU(torch.autograd.Function):
         _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(y), _b200.ptr(stats), P, geo.Cout,
                    geo.Cout, geo.Cout, BN_EPS, 1, 1 if have_stats else 0, _b200.ptr(_bn_workspace(dev, geo.Cout)),
                    _b200.stream())
-        ctx.save_for_backward(x, w, z, y, stats)
+        ctx.save_for_backward(x, w, z, y, stats, beta)
         ctx.geo = geo
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, z, y, stats = ctx.saved_tensors
+        x, w, z, y, stats, beta = ctx.saved_tensors
         geo = ctx.geo
         dev = x.device
         dy = dy.contiguous()
@@ -458,6 +465,11 @@ class _ConvBNReLU(torch.autograd.Function):
             dbeta = sums[:, 0].contiguous()
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
             _b200.call('lsi_b200_bn_relu_backward_staged', *args, 2, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        elif geo.Cout % 4 == 0 and geo.Cout <= 1024 and _BN_BWD_FAST:
+            # dense fast path: reads z and dy only (ReLU mask recomputed from z exactly as the forward kernel evaluates it)
+            _b200.call('lsi_b200_bn_relu_backward_z', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
+                       _b200.ptr(sums), P, geo.Cout, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+            dbeta = sums[:, 0].contiguous()
         else:
             _b200.call('lsi_b200_bn_relu_backward', _b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
                        _b200.ptr(sums), P, geo.Cout, geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0,
