@@ -236,6 +236,7 @@ def main():
     from lsi.geometry import ldi as ldi_utils
     from lsi.nnutils import helpers, nets, train_utils
     lib = _b200.lib()
+    numa_node = train_utils.bind_to_gpu_numa_node(local_rank)       # before any pinned allocation
 
     def barrier():
         if dist is not None:
@@ -404,10 +405,11 @@ def main():
     #     rendered views device->host (train_utils.HostViewPipeline: the copies of neighbouring steps overlap the kernels) ----
     del imgs
     torch.cuda.empty_cache()
-    hbatch = {'img': torch.tensor(img_host).pin_memory()}
+    # the source images are 8-bit data (PNG / JPEG decoders produce uint8): they cross the bus as uint8 and are scaled on the device
+    hbatch = {'img': torch.tensor(np.round(img_host * 255.0).astype(np.uint8)).pin_memory()}
     for name, key in (('k_s', 'k_s'), ('k_t', 'k_t'), ('rot', 'rot'), ('t', 't')):
         hbatch[name] = torch.tensor(host[key]).pin_memory()
-    pipe = train_utils.HostViewPipeline(opts, store, kw, B, H, W, dev, depth=2)
+    pipe = train_utils.HostViewPipeline(opts, store, kw, B, H, W, dev, depth=3, u8_input=True)
     checks = []
     e2e_steps = max(5, min(args.steps, 10))
     pipe.run([hbatch] * 3)
@@ -419,9 +421,10 @@ def main():
     assert len(checks) == e2e_steps and all(np.isfinite(c) for c in checks)
     e2e = {'value': world * B / e2e_s, 'unit': 'views/s', 'h2d_bytes_per_step': pipe.h2d_bytes(hbatch),
            'd2h_bytes_per_step': pipe.d2h_bytes(), 'ms_per_step': e2e_s * 1e3, 'steps': e2e_steps, 'conv_mode': head_mode,
+           'numa_node': numa_node,
            'api': 'lsi.nnutils.train_utils.HostViewPipeline.run (predict_ldi + lsi.geometry.ldi.forward_splat per batch) on pinned '
-                  'host images/cameras, rendered views copied back to pinned host memory every step; H2D of step k+1 and D2H of '
-                  'step k-1 overlap the kernels of step k'}
+                  'host uint8 images + float cameras, rendered views copied back to pinned host memory every step; H2D of step k+1 '
+                  'and D2H of step k-1 overlap the kernels of step k; 3 buffers deep; process bound to the GPU\'s NUMA node'}
     del pipe
 
     # --- strong scaling of BASELINE config 4 as written: global batch 64 split over the ranks (64 / world views per GPU) ----

@@ -91,6 +91,30 @@ def predict_ldi(img, opts, store, reuse):
     return [tex, masks, disps * opts.max_disp]
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process (its pipeline thread and the pinned host buffers it allocates afterwards: first touch) to the CPUs of
+    the NUMA node the GPU hangs off, read from sysfs.  With one process per GPU this keeps every rank's host<->device copies on
+    its own socket's memory controllers and PCIe root instead of all ranks sharing node 0.  Returns the node (or None when
+    sysfs does not expose it, e.g. in a container: nothing is changed then)."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 class HostViewPipeline(object):
     """Image -> LDI -> rendered target view (the predict + render path of ldi_pred_eval.py:117-224) over a sequence of
     HOST batches.  Three CUDA streams: while batch k runs its kernels, batch k+1's images and cameras are copied
@@ -100,10 +124,12 @@ class HostViewPipeline(object):
     per batch).
 
     batches: sequence of dicts of pinned host tensors {'img' [B,H,W,3], 'k_s','k_t','rot' [B,3,3], 't' [B,3] or [B,3,1]}.
-    on_result(k, img_host, wts_host) is called once batch k's views are in host memory (the buffers are recycled
-    after the callback returns)."""
+    'img' is float32 in [0,1], or -- u8_input=True -- the 8-bit image data as it comes out of a decoder (uint8): a quarter of the
+    host->device bytes; the scaling to [0,1] then runs on the device (lsi_b200_area_resize_u8 at unit scale, the kernel the KITTI
+    loader uses).  on_result(k, img_host, wts_host) is called once batch k's views are in host memory (the buffers are
+    recycled after the callback returns)."""
 
-    def __init__(self, opts, store, render_kw, batch, height, width, device, depth=2):
+    def __init__(self, opts, store, render_kw, batch, height, width, device, depth=2, u8_input=False):
         from lsi.geometry import ldi as ldi_utils
         self._render = ldi_utils.forward_splat
         if depth < 2:      # upload(k+1) is issued before batch k's kernels: with one slot it would overwrite batch k's inputs
@@ -113,7 +139,11 @@ class HostViewPipeline(object):
         ht, wt = int(height * ds), int(width * ds)
         dev = self.device
         self.pc = nn_helpers.pixel_coords(batch, height, width, _device=dev)
-        self.x = [torch.empty(batch, height, width, 3, device=dev) for _ in range(depth)]
+        self.u8 = bool(u8_input)
+        if self.u8 and batch * height > 65535:
+            raise ValueError('u8_input: batch * height must be <= 65535 (the batch is converted as one tall image)')
+        self.x = [torch.empty(batch, height, width, 3, device=dev, dtype=torch.uint8 if self.u8 else torch.float32) for _ in range(depth)]
+        self.xf = torch.empty(batch, height, width, 3, device=dev) if self.u8 else None      # converted images of the batch being computed
         self.cams = [dict(k_s=torch.empty(batch, 3, 3, device=dev), k_t=torch.empty(batch, 3, 3, device=dev),
                           rot=torch.empty(batch, 3, 3, device=dev), t=None) for _ in range(depth)]
         self.out_img = [torch.empty(1, batch, ht, wt, 3).pin_memory() for _ in range(depth)]
@@ -121,7 +151,7 @@ class HostViewPipeline(object):
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
     def h2d_bytes(self, batch):
-        return sum(batch[k].numel() * 4 for k in ('img', 'k_s', 'k_t', 'rot', 't'))
+        return sum(batch[k].numel() * batch[k].element_size() for k in ('img', 'k_s', 'k_t', 'rot', 't'))
 
     def d2h_bytes(self):
         return (self.out_img[0].numel() + self.out_wts[0].numel()) * 4
@@ -159,7 +189,12 @@ class HostViewPipeline(object):
             s = k % depth
             cur.wait_event(ready[s])
             with torch.no_grad():
-                ldi = predict_ldi(self.x[s], self.opts, self.store, reuse=True)
+                x = self.x[s]
+                if self.u8:          # 8-bit -> float32 / 255 on the device (the whole batch as one [B*H, W, 3] image, unit scale)
+                    bh, w = x.shape[0] * x.shape[1], x.shape[2]
+                    _b200.call('lsi_b200_area_resize_u8', _b200.ptr(x), bh, w, 3, _b200.ptr(self.xf), bh, w, 3, _b200.stream())
+                    x = self.xf
+                ldi = predict_ldi(x, self.opts, self.store, reuse=True)
                 c = self.cams[s]
                 c['t'].record_stream(cur)
                 img, wts = self._render(tuple(ldi), self.pc, c['k_s'], c['k_t'], c['rot'], c['t'], **self.kw)[:2]
