@@ -88,3 +88,48 @@ def test_train_step_tf32_runs_and_decreases_loss():
     losses = [tr.train_step(gb)[0].item() for _ in range(10)]
     assert np.isfinite(losses).all()
     assert losses[-1] < losses[0]
+
+
+def test_trainer_checkpoint_round_trip_on_gpu(tmp_path):
+    """Checkpoint I/O through the Trainer on the device (train_utils.py:172-200, 224-232): two steps, save, a FRESH Trainer (no
+    variables yet) resumes from the run directory and takes step 3; it must land where the uninterrupted trainer lands -- weights,
+    global_step, Adam slots and Adam's step count all survive."""
+    from lsi.nnutils import checkpoint as ck
+    from lsi.nnutils import nets, train_utils
+    nets.set_conv_mode('fp32')
+    try:
+        L, B, H, W = 1, 2, 128, 128
+        opts = train_utils.default_opts(n_layers=L, batch_size=B, img_height=H, img_width=W, learning_rate=1e-3)
+        gb = {k: torch.tensor(v, device='cuda') for k, v in _batch(B, H, W, 9).items()}
+        run = str(tmp_path / 'run')
+        tr = train_utils.Trainer(opts, store=nets.ParamStore(seed=4))
+        assert tr.init_from_checkpoints(run) == ('fresh', None)
+        tr.train_step(gb)
+        tr.train_step(gb)
+        path = tr.save(run, tr.step_count)
+        saved = ck.read_checkpoint(path)
+        assert int(saved['global_step']) == 2 and int(saved['adam_t']) == 2
+        assert 'encoder_decoder_unet/cnv1/weights/Adam' in saved and 'encoder_decoder_unet/cnv1/weights/Adam_1' in saved
+        loss_a = tr.train_step(gb)[0].item()
+        fresh = train_utils.Trainer(opts, store=nets.ParamStore(seed=77))          # different initialisation, no variables yet
+        what, src = fresh.init_from_checkpoints(run)
+        assert what == 'resumed' and src == path and fresh.step_count == 2 and fresh.adam_t == 2
+        assert sorted(fresh.store.vars) == sorted(tr.store.vars)
+        loss_b = fresh.train_step(gb)[0].item()
+        assert fresh.step_count == 3 and fresh.adam_t == 3
+        assert abs(loss_a - loss_b) <= 1e-5 * abs(loss_a)
+        # fp32 reductions are order-dependent (atomics), hence a tolerance far below one Adam step (lr = 1e-3)
+        d = (fresh.store.flat - tr.store.flat).abs().max().item()
+        assert d < 2e-5, d
+        # a resume WITHOUT the slots (the reference's own snapshots carry none) restarts Adam: the first update has magnitude lr again
+        ck.save_checkpoint(ck.checkpoint_path(str(tmp_path / 'ref'), 2), tr.store.vars, global_step=2)
+        ref_like = train_utils.Trainer(opts, store=nets.ParamStore(seed=78))
+        ref_like.restore(ck.checkpoint_path(str(tmp_path / 'ref'), 2))
+        before = {k: v.detach().clone() for k, v in ref_like.store.vars.items()}
+        ref_like.train_step(gb)
+        assert ref_like.adam_t == 1
+        w = 'encoder_decoder_unet/cnv1/weights'
+        step = (ref_like.store.vars[w].detach() - before[w]).abs()
+        assert abs(float(step[step > 0].median()) / opts.learning_rate - 1.0) < 0.05
+    finally:
+        nets.set_conv_mode('tf32')
