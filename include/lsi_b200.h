@@ -351,6 +351,25 @@ LSI_B200_API int lsi_b200_sigmoid_backward(const float* y, const float* dy, floa
 LSI_B200_API int lsi_b200_adam_step(float* params, const float* grads, float* m, float* v, long long n, float learning_rate,
                                     float beta1, float beta2, float epsilon, long long step, float grad_scale, void* stream);
 
+/* GPU-native synthetic planar-room generator (lsi/data/syntheticPlanes/data.py:372-420 with lsi/geometry/homography.py:95-156 and
+ * lsi/geometry/layers.py:29-118): for `batch` views of worlds of n_planes (<= 16) textured planes, one fused pass per target
+ * pixel over the planes -- hom_t2w [batch,n,9] takes target pixels to texture pixels (homography.inv_homography), dmat_t
+ * [batch,n,3] gives the plane's disparity at a target pixel (inv_homography_dmat); bilinear texture + mask sample, hard soft-z
+ * selection with a white background layer at min_disp.  Outputs: out_img [batch,h_out,w_out,3] (layers.compose, soft=False),
+ * out_disp_fg / out_disp_bg [batch,h_out,w_out,1] (layers.compose_depth, bg_layer False / True; either may be NULL).
+ * scratch_gmax: batch floats. */
+LSI_B200_API int lsi_b200_render_planes(const float* imgs_w, const float* masks_w, const float* hom_t2w, const float* dmat_t,
+                                        int batch, int n_planes, int h_tex, int w_tex, int h_out, int w_out, float min_disp,
+                                        float depth_softmax_temp, float* out_img, float* out_disp_fg, float* out_disp_bg,
+                                        float* scratch_gmax, void* stream);
+/* Procedural stand-ins for the PASCAL / SUN textures of the reference's generator: img [n,h,w,3] = clamp(0.5 + sum_k amp sin(fx x +
+ * fy y + phase)) per channel from params [n,3,n_waves,4]; mask [n,h,w,1] = 1 (kind 0) or a soft super-ellipse alpha (kind != 0). */
+LSI_B200_API int lsi_b200_procedural_texture(const float* params, const int* kind, int n_textures, int n_waves, int h, int w,
+                                             float* img, float* mask, void* stream);
+/* tf.image.resize_images(AREA) by an integer factor on float NHWC (data.py:364-368): box mean. */
+LSI_B200_API int lsi_b200_box_downsample(const float* in, float* out, int batch, int h, int w, int channels, int factor,
+                                         void* stream);
+
 /* KITTI loader data path (lsi/data/kitti/data.py:247-266): 8-bit HWC image (c_in channels, the first nc are used) -> float
  * [h_out, w_out, nc] in [0, 1], resized with the semantics of tf.image.resize_images(method=AREA) (exact area weighting,
  * any scale factor). */

@@ -94,6 +94,9 @@ SIGNATURES = {
     'lsi_b200_channel_sums_f64': (_I, [_P, _P, _LL, _I, _I, _P, _P]),
     'lsi_b200_copy_channels': (_I, [_P, _P, _LL, _I, _I, _I, _I, _P]),
     'lsi_b200_sigmoid_backward': (_I, [_P, _P, _P, _LL, _P]),
+    'lsi_b200_render_planes': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    'lsi_b200_procedural_texture': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    'lsi_b200_box_downsample': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'lsi_b200_area_resize_u8': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P]),
     'lsi_b200_adam_step': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _LL, _F, _P]),
 }

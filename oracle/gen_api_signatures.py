@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'ref_api_signatures.json')
 MODULES = {'lsi.geometry.ldi': 'lsi/geometry/ldi.py', 'lsi.geometry.sampling': 'lsi/geometry/sampling.py',
            'lsi.geometry.projection': 'lsi/geometry/projection.py', 'lsi.nnutils.helpers': 'lsi/nnutils/helpers.py',
-           'lsi.nnutils.nets': 'lsi/nnutils/nets.py', 'lsi.loss.loss': 'lsi/loss/loss.py'}
+           'lsi.nnutils.nets': 'lsi/nnutils/nets.py', 'lsi.loss.loss': 'lsi/loss/loss.py',
+           'lsi.geometry.homography': 'lsi/geometry/homography.py', 'lsi.geometry.layers': 'lsi/geometry/layers.py'}
 SCRIPTS = ['ldi_enc_dec.py', 'ldi_pred_eval.py']
 
 

@@ -241,7 +241,7 @@ def transpose(x, perm=None):
     return Tensor(t.permute(*perm))
 
 
-def matmul(a, b):
+def matmul(a, b, name=None):
     return Tensor(torch.matmul(_raw(a), _raw(b)))
 
 
@@ -268,7 +268,7 @@ def floor(x):
     return Tensor(torch.floor(_raw(x)))
 
 
-def exp(x):
+def exp(x, name=None):
     return Tensor(torch.exp(_raw(x)))
 
 
@@ -354,12 +354,12 @@ def reduce_min(x, axis=None, keep_dims=False):
     return Tensor(torch.amin(t, dim=axis, keepdim=keep_dims))
 
 
-def argmin(x, axis=None):
-    return Tensor(torch.argmin(_raw(x), dim=axis))
+def argmin(x, axis=None):      # [TF1.4] axis=None means axis 0 (math_ops.argmin), not a flattened arg-min
+    return Tensor(torch.argmin(_raw(x), dim=0 if axis is None else axis))
 
 
-def argmax(x, axis=None):
-    return Tensor(torch.argmax(_raw(x), dim=axis))
+def argmax(x, axis=None):      # [TF1.4] axis=None means axis 0 (layers.py:72 relies on it)
+    return Tensor(torch.argmax(_raw(x), dim=0 if axis is None else axis))
 
 
 def cumsum(x, axis=0):
