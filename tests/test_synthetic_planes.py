@@ -137,7 +137,7 @@ def test_data_loader_contract():
     B, H, W = 3, 64, 64
     ldi = (o['img_s'][None].contiguous(), torch.ones(1, B, H, W, 1, device='cuda'), o['disp_s_fg'][None].contiguous())
     img, wts = ldi_utils.forward_splat(ldi, helpers.pixel_coords(B, H, W), o['k_s'], o['k_t'], o['rot'], o['trans'], compose_layers=True,
-                                       bg_layer_disp=0.0, max_disp=1.0, zbuf_scale=50)
+                                       bg_layer_disp=0.0, max_disp=1.0, zbuf_scale=0)      # scale 0: unit weights, wts = coverage
     seen = (wts[0, ..., 0] > 0.5)
     err = (img[0] - o['img_t']).abs().mean(dim=-1)[seen]
     assert float(seen.float().mean()) > 0.5 and float(err.median()) < 0.08, (float(seen.float().mean()), float(err.median()))
