@@ -273,6 +273,11 @@ LSI_B200_API size_t lsi_b200_conv2d_stem_tc_workspace_bytes(void);
 LSI_B200_API int lsi_b200_conv2d_stem_tc(const lsi_b200_conv_desc* d, const float* in, const float* w, void* out, int out_f16,
                                          float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
 
+/* lsi_b200_conv2d_stem_tc in the split-precision mode: the im2col operand is built as (hi, lo) fp16 pairs from the fp32 image, the
+ * filter bank is split on the fly; out_kind 0: fp32 output, 2: split output (out_c_stride % 32 == 0).  Same workspace. */
+LSI_B200_API int lsi_b200_conv2d_stem_tc_s(const lsi_b200_conv_desc* d, const float* in, const float* w, void* out, int out_kind,
+                                           float* bn_stats, float bn_eps, void* workspace, size_t workspace_bytes, void* stream);
+
 /* y (__half, dense [n_pixels, channels]) = relu((x - mean) * rstd + beta) with given stats[c] = (mean, rstd); x is __half
  * (x_f16 != 0) or float; channels % 8 == 0.  The normalise pass of the fp16 mode (slim.batch_norm + ReLU, nets.py:263-272). */
 LSI_B200_API int lsi_b200_bn_relu_apply_h(const void* x, int x_f16, const float* beta, const float* stats, void* y,

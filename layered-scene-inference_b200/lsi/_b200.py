@@ -84,6 +84,7 @@ SIGNATURES = {
     'lsi_b200_conv2d_stem_tc_supported': (_I, [_CP]),
     'lsi_b200_conv2d_stem_tc_workspace_bytes': (_SZ, []),
     'lsi_b200_conv2d_stem_tc': (_I, [_CP, _P, _P, _P, _I, _P, _F, _P, _SZ, _P]),
+    'lsi_b200_conv2d_stem_tc_s': (_I, [_CP, _P, _P, _P, _I, _P, _F, _P, _SZ, _P]),
     'lsi_b200_bn_relu_apply_h': (_I, [_P, _I, _P, _P, _P, _LL, _I, _P]),
     'lsi_b200_bn_workspace_bytes': (_SZ, [_I]),
     'lsi_b200_conv2d_tc_bnstats': (_I, [_CP, _P, _I, _P, _I, _P, _P, _P, _F, _P, _SZ, _P]),

@@ -578,6 +578,22 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
             out = _Pending(z, stats, beta)
             return out if defer else out.materialize()
     srcs = [_materialize(t) for t in (x if pair else [x])]
+    if not pair and _STEM_TC and isinstance(srcs[0], torch.Tensor) and srcs[0].dtype == torch.float32 and not transposed:
+        # the 3-channel stem on tensor cores: im2col built in shared memory as (hi, lo) pairs, raw split output + statistics
+        xin = _b200.dev_f32(srcs[0], scope + ' input')
+        B, H, W, cin = xin.shape
+        geo = _Geometry(False, B, H, W, cin, cout, k, stride)
+        d = _b200.ConvDesc(**dict(geo.fwd, in_c_stride=cin))
+        if lib.lsi_b200_conv2d_stem_tc_supported(d) == 1:
+            w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
+            beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+            z = _SplitAct.empty(B, geo.Ho, geo.Wo, cout, xin.device)
+            stats = torch.empty(cout, 2, dtype=torch.float32, device=xin.device)
+            ws = _tc_workspace(xin.device, int(lib.lsi_b200_conv2d_stem_tc_workspace_bytes()))
+            _b200.call('lsi_b200_conv2d_stem_tc_s', d, _b200.ptr(xin), _b200.ptr(w), _b200.ptr(z.t), 2, _b200.ptr(stats), BN_EPS,
+                       _b200.ptr(ws), ws.numel(), _b200.stream())
+            out = _Pending(z, stats, beta)
+            return out if defer else out.materialize()
     if not pair and (srcs[0].shape[3] % 32 or cout % 32):
         # channel counts the split layout cannot hold (the 3-channel stem; nz = 1000 of the non-U-Net variant): exact fp32 kernels
         xin = _b200.dev_f32(to_float(srcs[0]), scope + ' input')
