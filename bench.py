@@ -215,6 +215,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-extras', action='store_true', help='skip the config 3 / config 5 / backward-kernel measurements')
+    ap.add_argument('--profile-step', action='store_true', help='run the warm-up and the timed steps only, then exit (launch lists under ncu)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -293,6 +294,11 @@ def main():
     clocks = sampler.stop()
     ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    if args.profile_step:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'views/s', 'ms_per_step': ms_per_step, 'steps': args.steps,
+                              'gpu_launches': int(launches), 'config': {'conv_mode': head_mode}, 'note': 'profile-step run'}))
+        return
 
     # --- per-kernel timing (CUDA events on the launching stream, live) -------------------------------------------
     lib.lsi_b200_kernel_timing_enable(1)
