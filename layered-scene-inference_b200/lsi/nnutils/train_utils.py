@@ -34,7 +34,14 @@ def default_opts(**kw):
         n_layers=2, batch_size=2, img_height=256, img_width=256, learning_rate=1e-4, beta1=0.9,
         self_cons_wt=1.0, indep_splat_wt=1.0, compose_splat_wt=1.0, splat_bdry_ignore=0.1, zbuf_scale=50.0,
         trg_splat_downsampling=0.5, disp_smoothness_wt=0.1, incr_depth_wt=10.0, l0_self_cons=False,
-        use_unet=True, n_layerwise_steps=3, pred_ldi_masks=False, bg_layer_disp=0.2, max_disp=1.0, dataset='synthetic')
+        use_unet=True, n_layerwise_steps=3, pred_ldi_masks=False, bg_layer_disp=0.2, max_disp=1.0, dataset='synthetic',
+        # logging / snapshotting and loop control (train_utils.py:38-57)
+        checkpoint_dir='/code/lsi/cachedir/snapshots/', pretrain_name='', pretrain_iter=100000, num_iter=100000, log_freq=5,
+        checkpoint_freq=50000, save_latest_freq=2000,
+        # data (ldi_enc_dec.py:48-82)
+        data_split='train', synth_ds_factor=1, n_obj_min=1, n_obj_max=4, n_box_planes=5, synth_dl_eval_data=False,
+        sun_imgs_dir=None, pascal_objects_dir=None, kitti_data_root='/datasets/kitti', kitti_dataset_variant='mview',
+        kitti_dl_disparities=False, debug_synth_texture=False)
     if kw.get('dataset') == 'kitti':
         o.bg_layer_disp, o.max_disp = 1e-3, 0.4
     o.__dict__.update(kw)
@@ -250,6 +257,59 @@ class Trainer(object):
         pc = nn_helpers.pixel_coords(b, h, w, _device=batch['imgs_src'].device)
         return loss_mod.view_synthesis_loss(ldi_src, ldi_trg, batch['imgs_src'], batch['imgs_trg'], pc, batch['k_s'],
                                             batch['k_t'], batch['rot_mat'], batch['trans_mat'], self.opts)
+
+    # ---- data + loop (train_utils.py:63-66, 149-222; ldi_enc_dec.py:130-137, 230-263) ------------------------------------
+    def define_data_loader(self):
+        """ldi_enc_dec.py:130-137: the synthetic planar-room generator or the KITTI stereo-pair loader."""
+        opts = self.opts
+        if opts.dataset == 'synthetic':
+            from lsi.data.syntheticPlanes import data as synthetic_planes
+            self.data_loader = synthetic_planes.DataLoader(opts)
+        elif opts.dataset == 'kitti':
+            from lsi.data.kitti import data as kitti_data
+            self.data_loader = kitti_data.DataLoader(opts)
+            self.data_loader.define_queues()
+            self.data_loader.preload_calib_files()
+        else:
+            raise ValueError('unknown dataset %r' % (opts.dataset,))
+
+    def feed(self):
+        """ldi_enc_dec.py:230-263: one batch from the loader, keyed like the reference's placeholders."""
+        if getattr(self.opts, 'debug_synth_texture', False):
+            raise NotImplementedError('debug_synth_texture (ground-truth disparities in place of the prediction) is not provided')
+        data = self.data_loader.forward(self.opts.batch_size)
+        img_src, img_trg, k_s, k_t, rot_mat, trans_mat = data[:6]
+        dev = self.store.device
+        f = lambda x: torch.as_tensor(x, dtype=torch.float32).to(dev)
+        return dict(imgs_src=f(img_src), imgs_trg=f(img_trg), k_s=f(k_s), k_t=f(k_t), rot_mat=f(rot_mat), trans_mat=f(trans_mat))
+
+    def train(self, on_log=None):
+        """train_utils.py:149-222 -- the training routine: seed 0, data loader, resume from the latest checkpoint of
+        opts.checkpoint_dir or else start from the pretrained net, then opts.num_iter steps with the reference's cadence: every
+        log_freq steps the losses are reported (on_log(global_step, total, parts); they are also appended to self.log -- the role
+        of the TF summaries), every save_latest_freq steps `model.latest` is written, every checkpoint_freq steps
+        `model-<global_step>`.  Returns self.log."""
+        import numpy as np_
+        opts = self.opts
+        torch.manual_seed(0)
+        np_.random.seed(0)
+        self.define_data_loader()
+        what, path = self.init_from_checkpoints(opts.checkpoint_dir, getattr(opts, 'pretrain_name', '') or None,
+                                                getattr(opts, 'pretrain_iter', 0))
+        self.log = [('init', what, path)]
+        for step in range(1, opts.num_iter + 1):
+            total, parts = self.train_step(self.feed())
+            gs = self.step_count
+            if step % opts.log_freq == 0:
+                rec = (gs, float(total), {k: float(v) for k, v in parts.items() if torch.is_tensor(v) or isinstance(v, float)})
+                self.log.append(rec)
+                if on_log is not None:
+                    on_log(*rec)
+            if step % opts.save_latest_freq == 0:
+                self.save(opts.checkpoint_dir, 'latest')
+            if step % opts.checkpoint_freq == 0:
+                self.save(opts.checkpoint_dir, gs)
+        return self.log
 
     # ---- checkpoints (train_utils.py:172-200, 224-232) -----------------------------------------------------------
     def _adam_slots(self):
