@@ -81,8 +81,9 @@ def split_sequences(data_split):
             'test': seq_names[n_train + n_val:n_all]}[data_split]
 
 
-def area_resize(img_u8, h, w, nc=3, device='cuda'):
-    """Decoded image (numpy / torch uint8 [H,W,C]) -> CUDA float [h,w,nc] in [0,1], AREA-resized (data.py:255-264)."""
+def area_resize(img_u8, h, w, nc=3, device='cuda', out=None):
+    """Decoded image (numpy / torch uint8 [H,W,C]) -> CUDA float [h,w,nc] in [0,1], AREA-resized (data.py:255-264); `out`: write
+    into this [h,w,nc] slice of a batch tensor instead of allocating."""
     t = torch.as_tensor(np.ascontiguousarray(img_u8)) if not torch.is_tensor(img_u8) else img_u8
     if t.dim() == 2:
         t = t.unsqueeze(-1)
@@ -91,7 +92,10 @@ def area_resize(img_u8, h, w, nc=3, device='cuda'):
     t = t.contiguous().to(device)
     if not t.is_cuda:
         raise RuntimeError('lsi_b200: area_resize runs on CUDA only (no CPU fallback)')
-    out = torch.empty(h, w, nc, dtype=torch.float32, device=t.device)
+    if out is None:
+        out = torch.empty(h, w, nc, dtype=torch.float32, device=t.device)
+    elif tuple(out.shape) != (h, w, nc) or not out.is_contiguous() or out.dtype != torch.float32 or out.device != t.device:
+        raise RuntimeError('lsi_b200: area_resize output slice must be a contiguous float32 [%d,%d,%d] tensor on %s' % (h, w, nc, t.device))
     _b200.call('lsi_b200_area_resize_u8', _b200.ptr(t), t.shape[0], t.shape[1], t.shape[2], _b200.ptr(out), h, w, nc, _b200.stream())
     return out
 
@@ -181,16 +185,24 @@ class DataLoader(object):
 
     read_calib_file = staticmethod(read_calib_file)
 
-    def define_queues(self):
-        """data.py:268-301 -- nothing to start: images are read on demand by forward()."""
-        return None
+    def define_queues(self, _threads=8, _prefetch=2):
+        """data.py:268-301 -- the reference starts TF filename queues, reader ops and a shuffle batch of capacity; here a pool of
+        decoder threads (PIL releases the GIL while inflating) that works `_prefetch` batches ahead of forward(), so decoding the
+        next batches overlaps the GPU work on the current one.  Without this call forward() decodes synchronously."""
+        import collections
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=int(_threads))
+        self._prefetch = int(_prefetch)
+        self._queued = collections.deque()
 
     def forward_instance(self, img_src, img_trg, src_shape, trg_shape, calib_data):
         """data.py:303-342."""
         k_s, k_t, rot, trans = stereo_cameras(calib_data, src_shape, trg_shape, self.h, self.w)
         return (img_src, img_trg, k_s, k_t, rot, trans)
 
-    def _load(self, path, nc):
+    @staticmethod
+    def _decode(path):
+        """PNG -> uint8 [H,W,C] (host)."""
         from PIL import Image
         img = np.asarray(Image.open(path))
         if img.ndim == 2:
@@ -198,30 +210,51 @@ class DataLoader(object):
         if img.dtype != np.uint8:
             # limitation: the SPS-stereo disparity PNGs of --kitti_dl_disparities are 16-bit; the resize kernel takes 8-bit data only
             raise RuntimeError('lsi_b200: %s is not an 8-bit image (16-bit disparity PNGs are not supported)' % path)
-        return area_resize(img, self.h, self.w, nc), img.shape
+        return np.ascontiguousarray(img)
+
+    def _schedule(self, bs):
+        """Next bs samples of the epoch order: (ids, [decoded-image futures or arrays per sample])."""
+        ids = [int(self._order[(self._cursor + b) % len(self._order)]) for b in range(bs)]
+        self._cursor = (self._cursor + bs) % len(self._order)
+        pool = getattr(self, '_pool', None)
+        run = (lambda p: pool.submit(self._decode, p)) if pool is not None else (lambda p: self._decode(p))
+        jobs = []
+        for i in ids:
+            paths = [self.img_list_src[i], self.img_list_trg[i]]
+            if self.output_disparities:
+                paths += [self.img_list_disp_src[i], self.img_list_disp_trg[i]]
+            jobs.append([run(p) for p in paths])
+        return ids, jobs
 
     def forward(self, bs):
         """data.py:344-390 -- (img_s, img_t, k_s, k_t, rot, trans[, disp_s, disp_t]) for the next bs samples of the epoch
         order, as CUDA tensors (images [bs,h,w,3] float32 in [0,1], cameras float32)."""
         if len(self.img_list_src) == 0:
             raise RuntimeError('lsi_b200: no KITTI images under %s' % self.root_dir)
-        ids = [int(self._order[(self._cursor + b) % len(self._order)]) for b in range(bs)]
-        self._cursor = (self._cursor + bs) % len(self._order)
+        queued = getattr(self, '_queued', None)
+        if queued is None:
+            ids, jobs = self._schedule(bs)
+        else:
+            if queued and len(queued[0][0]) != bs:          # batch size changed: drop what was decoded ahead (and rewind the order)
+                self._cursor = (self._cursor - sum(len(q[0]) for q in queued)) % len(self._order)
+                queued.clear()
+            while len(queued) < 1 + self._prefetch:
+                queued.append(self._schedule(bs))
+            ids, jobs = queued.popleft()
         self.src_image_names = [self.img_list_src[i] for i in ids]
-        cols = [[] for _ in range(6)]
-        disp = [[], []]
-        for i in ids:
-            img_s, s_shape = self._load(self.img_list_src[i], 3)
-            img_t, t_shape = self._load(self.img_list_trg[i], 3)
-            inst = self.forward_instance(img_s, img_t, s_shape, t_shape, self.cam_calibration[self.seq_id_list[i]])
-            for c, v in zip(cols, inst):
+        dev = torch.device('cuda')
+        get = lambda j: j.result() if hasattr(j, 'result') else j
+        imgs = [torch.empty(bs, self.h, self.w, 3, dtype=torch.float32, device=dev) for _ in range(2)]
+        disps = [torch.empty(bs, self.h, self.w, 1, dtype=torch.float32, device=dev) for _ in range(2)] if self.output_disparities else []
+        cams = [[] for _ in range(4)]
+        for b, (i, job) in enumerate(zip(ids, jobs)):
+            dec = [get(j) for j in job]
+            area_resize(dec[0], self.h, self.w, 3, out=imgs[0][b])          # one launch per image (KITTI frames differ in size), written
+            area_resize(dec[1], self.h, self.w, 3, out=imgs[1][b])          # straight into the batch tensor
+            inst = self.forward_instance(None, None, dec[0].shape, dec[1].shape, self.cam_calibration[self.seq_id_list[i]])
+            for c, v in zip(cams, inst[2:]):
                 c.append(v)
-            if self.output_disparities:
-                disp[0].append(self._load(self.img_list_disp_src[i], 1)[0])
-                disp[1].append(self._load(self.img_list_disp_trg[i], 1)[0])
-        dev = cols[0][0].device
-        out = [torch.stack(cols[0]), torch.stack(cols[1])]
-        out += [torch.tensor(np.stack(c), dtype=torch.float32, device=dev) for c in cols[2:]]
-        if self.output_disparities:
-            out += [torch.stack(disp[0]), torch.stack(disp[1])]
+            for k in range(len(disps)):
+                area_resize(dec[2 + k], self.h, self.w, 1, out=disps[k][b])
+        out = imgs + [torch.tensor(np.stack(c), dtype=torch.float32, device=dev) for c in cams] + disps
         return out

@@ -131,3 +131,17 @@ def test_loader_forward_end_to_end(tmp_path):
         assert np.allclose(k_s[b].cpu().numpy(), ks, rtol=1e-6) and np.allclose(trans[b].cpu().numpy(), t, rtol=1e-6, atol=1e-9)
     again = dl.forward(3)                                            # the epoch order moves on and wraps
     assert dl.src_image_names and again[0].shape == (3, 16, 48, 3)
+
+
+@pytest.mark.gpu
+def test_prefetching_loader_equals_synchronous_loader(tmp_path):
+    """define_queues() starts a decoder pool that works batches ahead; the batches (and their order, also across a batch-size
+    change) must be exactly those of the synchronous loader."""
+    from lsi.data.kitti import data as kd
+    _fake_tree(str(tmp_path))
+    sync = kd.DataLoader(_opts(str(tmp_path), 'val', bs=2)); sync.preload_calib_files()
+    pre = kd.DataLoader(_opts(str(tmp_path), 'val', bs=2)); pre.define_queues(_threads=3, _prefetch=2); pre.preload_calib_files()
+    for bs in (2, 2, 3, 2):
+        a, b = sync.forward(bs), pre.forward(bs)
+        assert sync.src_image_names == pre.src_image_names
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
