@@ -159,11 +159,20 @@ def test_conv_fp16_operands(B, H, W, Cin, Cout, k, s, mode, split, out_f16):
     (1, 16, 32, 64, 128, 3, 2),
     (2, 8, 16, 32, 64, 4, 2),        # transposed conv: big = dout (2H x 2W, 32 ch), small = input (H x W, 64 ch)
     (1, 8, 16, 40, 24, 3, 1),        # channel counts that are not multiples of 32
+    (2, 40, 70, 32, 32, 3, 1),       # several pixel tiles per split, ragged
+    (1, 24, 48, 64, 64, 5, 1),       # 5 taps per row: two M tiles per filter row, two accumulator groups
+    (1, 16, 32, 32, 64, 7, 1),       # 14 M tiles in groups of 7
+    (1, 16, 32, 64, 256, 3, 1),      # four B blocks per N tile, two N tiles
+    (1, 4, 14, 128, 128, 3, 1),      # image narrower than the tile
 ])
-def test_wgrad_tensor_core(B, H, W, Ca, Cb, k, s):
+@pytest.mark.parametrize('halo', [True, False])
+def test_wgrad_tensor_core(B, H, W, Ca, Cb, k, s, halo, monkeypatch):
     """lsi_b200_conv2d_wgrad_tc against the fp32 weight-gradient kernel; sizes are those of the strided-gather side
-    (H x W, Ca channels) like the descriptor's *_in fields."""
+    (H x W, Ca channels) like the descriptor's *_in fields.  halo: the stride-1 halo-tile kernel (default) / the per-tap kernel."""
     from lsi import _b200
+    if not halo and s != 1:
+        pytest.skip('stride-2 shapes always take the per-tap kernel')
+    monkeypatch.setenv('LSI_B200_WGRAD_HALO', '1' if halo else '0')
     from lsi.nnutils.nets import same_pad
     torch.manual_seed(Ca + Cb + k)
     Ho, Wo = -(-H // s), -(-W // s)
