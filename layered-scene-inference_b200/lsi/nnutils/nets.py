@@ -250,6 +250,12 @@ def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=Non
     d = _b200.ConvDesc(**desc_kw)
     lib = _b200.lib()
     ca = d.c_in if c_in_a is None else c_in_a
+    if (_HALO and _HALO_GENERIC and _tc_mode() and inp_b is None and inp.dtype == torch.float32 and out.dtype == torch.float32
+            and inp.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and lib.lsi_b200_conv2d_halo_supported(d) == 1):
+        # full-resolution 32/64-channel head layers, also inside the training step (forward convs, the data gradient of
+        # upcnv1b): resident filter bank + one halo box per tile instead of one box per tap
+        _conv_halo(d, inp, w, out, bias=bias, out_stats=bn_stats)
+        return bn_stats is not None
     if _tc_ok(d, ca, inp, inp_b):
         nws = int(lib.lsi_b200_conv2d_tc_workspace_bytes(d))
         ws = _tc_workspace(inp.device, nws)
@@ -286,6 +292,7 @@ _HALO = os.environ.get('LSI_B200_CONV_HALO', '1') != '0'
 _HALO_F16_STORE = os.environ.get('LSI_B200_HALO_F16_STORE', '1') != '0'
 _STEM_TC = os.environ.get('LSI_B200_STEM_TC', '1') != '0'
 _HALO_CONCAT = os.environ.get('LSI_B200_HALO_CONCAT', '1') != '0'
+_HALO_GENERIC = os.environ.get('LSI_B200_HALO_GENERIC', '1') != '0'      # halo kernel from _conv (training step)
 _OUT_SCALE_CACHE = {}
 _BN_BWD_FAST = os.environ.get('LSI_B200_BN_BWD_FAST', '1') != '0'
 _SPLIT_UPCONV_MATERIALIZE = os.environ.get('LSI_B200_SPLIT_UPCONV_MATERIALIZE', '1') != '0'
