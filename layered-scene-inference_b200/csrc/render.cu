@@ -11,6 +11,7 @@
 #include "render_fast.cuh"
 #include "render_stream.cuh"
 #include "render_rowowner.cuh"
+#include "render_rowgather.cuh"
 
 namespace lsi {
 
@@ -448,6 +449,92 @@ static int launch_stream(const FastParams& f, bool has_mask, bool packed, cudaSt
   return LSI_B200_OK;
 }
 
+
+static bool rowgather_enabled() {
+  static int on = -1;
+  if (on < 0) on = env_int("LSI_B200_ROWGATHER", 1) != 0 ? 1 : 0;
+  return on == 1;
+}
+
+// Row-gather splat (render_rowgather.cuh): persistent CTAs, each a contiguous range of (image, output layer, target row)
+// tasks.  Returns LSI_B200_OK with *launched = false when the shape does not fit the kernel (the caller falls back).
+static int launch_rowgather(const lsi_b200_splat_desc* d, const float* tex, const float* disp, const float* mask,
+                            const float* mats, const int* flags, float* img, float* wts, bool packed, bool all_flagged,
+                            cudaStream_t st, bool* launched) {
+  *launched = false;
+  const int w_lists = d->w_s > d->w_t + 1 ? d->w_s : d->w_t + 1;                       // pixels per row / lists per row (w_t + 1)
+  const int threads = ((w_lists + kRgPerThread - 1) / kRgPerThread + 31) / 32 * 32;   // consumer threads
+  if (threads > kRgMaxThreads || d->w_s > 65534) return LSI_B200_OK;
+  const int l_outer = d->compose_layers ? 1 : d->n_layers;
+  if ((long long)l_outer * d->batch * d->h_t * d->w_t >= (1ll << 32)) return LSI_B200_OK;
+  static int sms = 0, stages_env = 0;
+  if (!sms) {
+    int dev = 0;
+    LSI_CUDA(cudaGetDevice(&dev));
+    LSI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    stages_env = env_int("LSI_B200_ROWGATHER_STAGES", 0);
+  }
+  RowGatherParams p;
+  p.tex = tex; p.disp = disp; p.mask = mask; p.mats = mats; p.flags = flags; p.img = img; p.wts = wts;
+  p.L = d->n_layers; p.B = d->batch; p.H = d->h_s; p.W = d->w_s; p.h_t = d->h_t; p.w_t = d->w_t;
+  p.l_outer = l_outer;
+  p.all_flagged = all_flagged ? 1 : 0;
+  p.ds = d->trg_downsampling; p.inv_max_disp = 1.f / d->max_disp;
+  p.k2 = d->zbuf_scale * 1.4426950408889634f; p.k2h = 0.5f * p.k2;
+  p.nb = d->compose_layers ? (float)d->n_layers * bg_weight(d) : bg_weight(d);
+  p.tasks = (long long)d->batch * p.l_outer * d->h_t;
+  p.threads = threads;
+  const bool small = threads + 32 <= 256;
+  size_t off = 128;                                         // full / empty mbarriers (<= 8 stages)
+  p.off_desc = (int)off; off += 8 * 32;                     // item descriptors
+  const size_t wpad = (size_t)kRgPerThread * threads;       // every per-pixel array is padded to 4 entries per consumer thread
+  p.off_head = (int)off; off = align_up(off + ((size_t)d->w_t + 34) * 4, 16);
+  p.off_next = (int)off; off = align_up(off + wpad * 2, 16);
+  p.off_wl = (int)off; off = align_up(off + wpad * 4, 16);
+  p.off_wr = (int)off; off = align_up(off + wpad * 4, 16);
+  p.off_xpose = (int)off; off += (size_t)(threads / 32) * 384;
+  p.off_bnd = (int)off; off += (size_t)kRgPerThread * (threads / 32) * 16;
+  p.off_val4 = (int)off; if (!packed) off += wpad * 16;
+  off = align_up(off, 128);
+  p.off_ring = (int)off;
+  p.stage_bytes = (int)align_up(wpad * (16 + (mask ? 4 : 0)), 128);
+  const int want_ctas = small ? LSI_RG_MIN_CTAS : 1;
+  int stages = stages_env > 0 ? stages_env : 3;
+  if (stages > 8) stages = 8;
+  while (stages > 2 && (off + (size_t)stages * p.stage_bytes + 1024) * want_ctas > 232448) --stages;
+  const size_t smem = off + (size_t)stages * p.stage_bytes;
+  if (smem > 232448 - 1024) return LSI_B200_OK;            // row too wide for one CTA's shared memory
+  p.stages = stages;
+  int per_sm = (int)(232448 / (smem + 1024));
+  if (per_sm > want_ctas) per_sm = want_ctas;
+  long long grid = (long long)sms * per_sm;
+  if (grid > p.tasks) grid = p.tasks;
+  const int ki = (small ? 0 : 4) | (mask ? 2 : 0) | (packed ? 1 : 0);
+  void (*kern)(const RowGatherParams) = nullptr;
+  switch (ki) {
+    case 0: kern = splat_fwd_rowgather_kernel<256, false, false>; break;
+    case 1: kern = splat_fwd_rowgather_kernel<256, false, true>; break;
+    case 2: kern = splat_fwd_rowgather_kernel<256, true, false>; break;
+    case 3: kern = splat_fwd_rowgather_kernel<256, true, true>; break;
+    case 4: kern = splat_fwd_rowgather_kernel<544, false, false>; break;
+    case 5: kern = splat_fwd_rowgather_kernel<544, false, true>; break;
+    case 6: kern = splat_fwd_rowgather_kernel<544, true, false>; break;
+    default: kern = splat_fwd_rowgather_kernel<544, true, true>; break;
+  }
+  static size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (smem > smem_set[ki]) {
+    LSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[ki] = smem;
+  }
+  {
+    ScopedTiming tm(kSplatFwd, st);
+    kern<<<(unsigned)grid, threads + 32, smem, st>>>(p);
+  }
+  LSI_LAUNCH_CHECK();
+  *launched = true;
+  return LSI_B200_OK;
+}
+
 template <typename K, typename P>
 static void launch3(K kern, dim3 grid, dim3 block, cudaStream_t st, const P& p) { kern<<<grid, block, 0, st>>>(p); }
 
@@ -502,7 +589,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   // fast path: standard grid, no focal shift, no trg_disp, 16-byte aligned rows, planar (3/1/1) or packed (4/4) layout
   const bool packed = d->tex_px_stride == 4 && d->disp_px_stride == 4 && disp == tex + 3;
   const bool planar = d->tex_px_stride == 3 && d->disp_px_stride == 1;
-  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant == 3 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
+  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant == 3 || d->variant == 5 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
                     (!mask || d->mask_px_stride == 1) && (!packed || ((uintptr_t)tex & 15) == 0) && d->h_s <= 65535 &&
                     bc_fits_grid;
   // rectified-stereo pose class: warp-owned target rows in shared memory, written once (render_rowowner.cuh); images of
@@ -510,10 +597,25 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   const int* skip = nullptr;
   const bool fast_eligible = fast;
   // streaming kernel (render_stream.cuh): bulk copies need 16-byte aligned row segments
-  const bool use_stream = fast && d->variant == 0 && !rowowner_enabled() && stream_enabled() && ((uintptr_t)tex & 15) == 0 &&
+  const bool use_stream_shape = fast && ((uintptr_t)tex & 15) == 0 &&
                       (packed || (d->w_s % 4 == 0 && ((uintptr_t)disp & 15) == 0)) &&
                       (!mask || (d->w_s % 4 == 0 && ((uintptr_t)mask & 15) == 0));
-  if (fast_eligible && (d->variant == 2 || rowowner_enabled())) {
+  const bool use_stream = use_stream_shape && (d->variant == 0 || d->variant == 5) && !rowowner_enabled() && stream_enabled();
+  // rectified pose class, default: row-gather kernel (render_rowgather.cuh) -- target rows owned by CTAs, the scatter inverted
+  // in shared memory, normalisation fused.  variant 5 = the caller knows (from these flags, read back earlier for the same
+  // camera tensors) that every image is in the class: the reduction kernels below are not launched at all (a hint: shapes the
+  // kernel does not take run the default path).
+  const bool gather_ok = use_stream_shape && (d->variant == 0 || d->variant == 5) && rowgather_enabled() && !rowowner_enabled();
+  if (gather_ok) {
+    bool launched = false;
+    if (int rc = launch_rowgather(d, tex, disp, mask, mats, rect_flags, trg_img, trg_wts, packed, d->variant == 5, st, &launched))
+      return rc;
+    if (launched) {
+      if (d->variant == 5) return LSI_B200_OK;
+      skip = rect_flags;
+    }
+  }
+  if (!skip && fast_eligible && (d->variant == 2 || rowowner_enabled())) {
     int R = (int)(14336 / ((size_t)d->w_t * 16));
     if (R > 4) R = 4;
     if (R > d->h_t) R = d->h_t;

@@ -1,0 +1,377 @@
+// Row-gather forward splat for the rectified pose class (n == 1, y' independent of x and d, rows keep their order:
+// stereo pairs, the KITTI configurations -- BASELINE config 4).  The default forward path for that class.
+//
+// What the reduction kernels (render_stream.cuh) pay for: one 16-byte `red.global` per pixel-layer cell through the L2
+// atomic unit (as much payload as the HBM read, 27 sectors per warp request on scattered disparities), an L2-resident
+// accumulator that has to be zeroed and re-read, and a separate normalise pass.  In this pose class a source row lands on
+// one or two fixed TARGET rows with row-constant vertical weights, so the scatter is a 1-D problem per target row and can
+// be inverted inside shared memory:
+//
+//   * a CTA owns whole target rows (a contiguous range of (image, output layer, target row) tasks).  A producer warp walks
+//     the tasks, and for every (source row, layer) that touches the row -- an *item* -- writes a small descriptor (matrix row,
+//     vertical weight, output offset) and streams the W pixels x 16 B into a shared-memory ring with 1-D bulk copies
+//     (cp.async.bulk, mbarrier completion; full / empty barriers per slot);
+//   * the consumer warps run two passes per item:
+//       pass 1 (thread = source pixel): projection, z-buffer weight, horizontal corner weights, thresholds; the weighted
+//         value (w*rgb, w) replaces the pixel in the stage, the two corner weights go to small arrays, and the pixel links
+//         itself into the list of its left target cell with ONE integer ATOMS.EXCH (measured 2 SM-cycles per warp
+//         instruction on B200, tools/micro/atoms_bench.cu -- the float atomics a shared-memory scatter would need are CAS
+//         loops).  List heads carry a 16-bit generation tag, so they are never cleared between items;
+//       pass 2 (thread = target cell): walks the list of its own cell (left weights) and of its left neighbour's cell
+//         (right weights) and accumulates in REGISTERS -- a gather, no float atomics anywhere;
+//   * after the last item of a row the thread normalises (ldi.py:165-173, bg canvas folded in) and stores its cells once,
+//     through a warp-private transposition buffer so that the stores are 128-bit.
+//
+// HBM traffic = the algorithmic bytes (every source row read once when it maps to one target row, otherwise again through
+// L2; every target pixel written once); no accumulator, no memset, no normalise launch.  Same per-pixel formulas as
+// render_stream.cuh (projection / z-weight / threshold expressions), summation order differs.
+#pragma once
+#include "render_stream.cuh"
+
+namespace lsi {
+
+#ifndef LSI_RG_MIN_CTAS
+#define LSI_RG_MIN_CTAS 3
+#endif
+constexpr int kRgPerThread = 4;        // source pixels (pass 1) and target cells (pass 2, register accumulators) per consumer thread
+constexpr int kRgMaxThreads = 512;     // consumer threads: max(W, w_t) <= 2048
+constexpr unsigned kRgNil = 0xffffu;
+constexpr uint32_t kRgData = 1u, kRgLast = 2u, kRgEnd = 4u, kRgNan = 8u;
+
+struct RowGatherParams {
+  const float* tex; const float* disp; const float* mask; const float* mats; const int* flags;
+  float* img; float* wts;
+  int L, B, H, W, h_t, w_t;
+  int l_outer;              // output layers: 1 (compose) or L
+  int all_flagged;          // caller asserts that every image is in the class: an unflagged image gets NaNs (loud), no fallback ran
+  float ds, inv_max_disp, k2, k2h, nb;
+  int threads;              // consumer threads (multiple of 32); the producer warp follows them
+  int stages, stage_bytes;
+  int off_desc, off_val4, off_wl, off_wr, off_head, off_next, off_xpose, off_bnd, off_ring;   // shared-memory layout (bytes)
+  long long tasks;          // B * l_outer * h_t
+};
+
+// ---- shared memory through 32-bit addresses (generic pointers cost an address-space conversion per access) -----------------
+__device__ __forceinline__ float rg_lds(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t rg_lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t rg_lds_u16(uint32_t a) {
+  unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ float4 rg_lds4(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void rg_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void rg_sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void rg_sts4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t rg_exch(uint32_t a, uint32_t v) {
+  uint32_t o; asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o;
+}
+__device__ __forceinline__ void rg_sts_u16(uint32_t a, uint32_t v) {
+  asm volatile("{\n.reg .b16 h;\ncvt.u16.u32 h, %1;\nst.shared.u16 [%0], h;\n}" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void rg_bar_consumers(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
+__device__ __forceinline__ void rg_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void rg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rg_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
+}
+__device__ __forceinline__ void rg_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+// vertical weight of source row i on target row r: the expressions of row_setup() (render_stream.cuh), bit for bit
+__device__ __forceinline__ float rg_row_weight(float M5, float M6, float ds, int h_t, int r, int i) {
+  const float ys = (float)i + 0.5f;
+  const float bv = fmaf(M5, ys, 0.f) + M6;
+  const AxisW ay = axis_weights(fmaf(bv, ds, -0.5f), h_t);
+  return ay.i0 == r ? ay.w0 : (ay.i0 + 1 == r ? ay.w1 : 0.f);
+}
+
+// ---- producer (one thread): tasks -> items -> descriptors + bulk copies -------------------------------------------------------
+template <bool kHasMask, bool kPacked>
+__device__ __forceinline__ void rg_producer(const RowGatherParams& p, uint32_t sbase, long long t0, long long t1) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  const int per_img = p.l_outer * p.h_t;
+  int b = (int)(t0 / per_img);
+  int rem = (int)(t0 - (long long)b * per_img);
+  int lo = rem / p.h_t, r = rem - lo * p.h_t;
+  const size_t n_src = (size_t)p.H * p.W;
+  const uint32_t n_trg = (uint32_t)p.h_t * p.w_t;
+  const uint32_t W = (uint32_t)p.W;
+  int slot = 0;
+  uint32_t parity = 0;
+  long long emitted = 0;
+  // one descriptor + (optionally) one row of pixels into the next slot
+  auto emit = [&](uint32_t kind, float4 m0, float ys, float wy, uint32_t out_row, int l, int i) {
+    const uint32_t full = sbase + slot * 8, empty = sbase + 64 + slot * 8;
+    if (emitted >= p.stages) rg_mbar_wait(empty, parity ^ 1);       // the consumers have released this slot's previous item
+    const uint32_t dsc = sbase + p.off_desc + slot * 32;
+    rg_sts4(dsc, m0.x, m0.y, m0.z, m0.w);
+    rg_sts4(dsc + 16, ys, wy, __uint_as_float(out_row), __uint_as_float(kind));
+    if (kind & kRgData) {
+      const uint32_t stage = sbase + p.off_ring + slot * p.stage_bytes;
+      const size_t img = ((size_t)l * p.B + b) * n_src + (size_t)i * p.W;
+      rg_mbar_expect_tx(full, W * (16u + (kHasMask ? 4u : 0u)));
+      if (kPacked) {
+        rg_bulk(stage, reinterpret_cast<const unsigned char*>(p.tex) + img * 16, W * 16, full, policy);
+      } else {
+        rg_bulk(stage, reinterpret_cast<const unsigned char*>(p.tex) + img * 12, W * 12, full, policy);
+        rg_bulk(stage + W * 12, p.disp + img, W * 4, full, policy);
+      }
+      if (kHasMask) rg_bulk(stage + (uint32_t)(kRgPerThread * 16) * p.threads, p.mask + img, W * 4, full, policy);
+    } else {
+      rg_mbar_arrive(full);
+    }
+    ++emitted;
+    if (++slot == p.stages) { slot = 0; parity ^= 1; }
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long task = t0; task < t1; ++task) {
+    const uint32_t out_row = ((uint32_t)lo * p.B + b) * n_trg + (uint32_t)r * p.w_t;
+    if (p.flags[b]) {
+      const float4* mp = reinterpret_cast<const float4*>(p.mats + (size_t)b * 16);
+      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      const float M5 = m1.y, M6 = m1.z;
+      // y'(i) = (M5*(i+0.5) + M6)*ds - 0.5 is increasing in i (the class flag requires M5 > 0); rows with floor(y') in {r-1, r}
+      const float a = M5 * p.ds, c = M6 * p.ds - 0.5f;
+      const float lo_f = floorf(((float)(r - 1) - c) / a - 0.5f) - 1.f, hi_f = ceilf(((float)(r + 1) - c) / a - 0.5f) + 1.f;
+      const int i_lo = (int)fminf(fmaxf(lo_f, 0.f), (float)(p.H - 1));
+      const int i_hi = (int)fminf(fmaxf(hi_f, -1.f), (float)(p.H - 1));
+      const int l_begin = p.l_outer == 1 ? 0 : lo, l_end = p.l_outer == 1 ? p.L : lo + 1;
+      // the last (row, layer) with weight closes the task: look one row ahead
+      int i = i_lo;
+      float wy = 0.f;
+      while (i <= i_hi && (wy = rg_row_weight(M5, M6, p.ds, p.h_t, r, i)) == 0.f) ++i;
+      if (i > i_hi) {
+        emit(kRgLast, zero4, 0.f, 0.f, out_row, 0, 0);                 // nothing lands on this row: background only
+      } else {
+        while (i <= i_hi) {
+          int i_next = i + 1;
+          float wy_next = 0.f;
+          while (i_next <= i_hi && (wy_next = rg_row_weight(M5, M6, p.ds, p.h_t, r, i_next)) == 0.f) ++i_next;
+          const bool last_row = i_next > i_hi;
+          for (int l = l_begin; l < l_end; ++l)
+            emit(kRgData | ((last_row && l == l_end - 1) ? kRgLast : 0u), m0, (float)i + 0.5f, wy, out_row, l, i);
+          i = i_next; wy = wy_next;
+        }
+      }
+    } else if (p.all_flagged) {
+      emit(kRgLast | kRgNan, zero4, 0.f, 0.f, out_row, 0, 0);
+    }
+    if (++r == p.h_t) { r = 0; if (++lo == p.l_outer) { lo = 0; ++b; } }
+  }
+  emit(kRgEnd, zero4, 0.f, 0.f, 0u, 0, 0);
+}
+
+// kCtaThreads = consumer threads + the producer warp: 256 (rows up to 896 pixels, 4 CTAs per SM) or 544 (up to 2048, 2 per SM)
+template <int kCtaThreads, bool kHasMask, bool kPacked>
+__global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_CTAS : 1) splat_fwd_rowgather_kernel(const RowGatherParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = st_smem_u32(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = p.threads;
+  // [0,64): full barriers, [64,128): empty barriers
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + s * 8));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + 64 + s * 8));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = tid; c < p.w_t + 34; c += blockDim.x) rg_sts_u32(sbase + p.off_head + c * 4, 0u);      // w_t + 1 lists, a never-tagged word, 32 dummies
+  __syncthreads();
+  const long long t0 = p.tasks * blockIdx.x / gridDim.x, t1 = p.tasks * (blockIdx.x + 1) / gridDim.x;
+
+  if (tid >= T) {                                   // producer warp
+    if (tid == T) rg_producer<kHasMask, kPacked>(p, sbase, t0, t1);
+    return;
+  }
+
+  // ---- consumers
+  const int w_t_ = p.w_t;
+  const uint32_t s_wl = sbase + p.off_wl, s_wr = sbase + p.off_wr, s_head = sbase + p.off_head, s_next = sbase + p.off_next;
+  const uint32_t s_xpose = sbase + p.off_xpose + warp * 384, s_bnd = sbase + p.off_bnd;
+  const uint32_t s_dummy = s_head + (w_t_ + 2 + lane) * 4;      // per-lane dummy list head (words w_t + 2 ... w_t + 33)
+  const int W = p.W, w_t = p.w_t, nwarps = T >> 5;
+  const float ds = p.ds, inv_md = p.inv_max_disp, k2 = p.k2, k2h = p.k2h;
+  const float x_hi = (float)w_t + 1.f, xs0 = (float)tid + 0.5f, fT = (float)T;
+  const bool vec_out = (w_t & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.img) & 15) == 0);
+  // thread j walks list j (source pixels whose left cell is j - 1, right cell j): accL -> cell j - 1, accR -> cell j (its own)
+  float4 accL[kRgPerThread], accR[kRgPerThread];
+#pragma unroll
+  for (int k = 0; k < kRgPerThread; ++k) { accL[k] = make_float4(0.f, 0.f, 0.f, 0.f); accR[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  int slot = 0;
+  uint32_t parity = 0;
+  uint32_t gen = 0;
+
+  for (;;) {
+    rg_mbar_wait(sbase + slot * 8, parity);
+    const uint32_t dsc = sbase + p.off_desc + slot * 32;
+    const float4 d1 = rg_lds4(dsc + 16);
+    const uint32_t kind = __float_as_uint(d1.w);
+    if (kind & kRgEnd) break;
+    if (kind & kRgData) {
+      const float4 M = rg_lds4(dsc);
+      if (++gen == 0x10000u) {           // generation tags wrapped: forget every list
+        rg_bar_consumers(T);
+        for (int c = tid; c < w_t + 34; c += T) rg_sts_u32(s_head + c * 4, 0u);
+        gen = 1;
+        rg_bar_consumers(T);
+      }
+      const uint32_t tag = gen << 16;
+      const uint32_t s_stage = sbase + p.off_ring + slot * p.stage_bytes;
+      const uint32_t s_val = kPacked ? s_stage : sbase + p.off_val4;
+      const float ys = d1.x, wy = d1.y;
+      // ---- pass 1: thread = source pixel.  Every array is padded to kRgPerThread * T entries: pixels past the row end compute
+      // on whatever the slot holds and store into their own padding; their list insertion goes to a per-lane dummy head.
+      // Written in phases over the thread's four pixels (loads / arithmetic / stores / exchanges / links): the shared-memory
+      // accesses are ordered asm statements, so this is what lets four independent chains overlap.
+      float4 v[kRgPerThread];
+      float mk[kRgPerThread];
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        const int px = tid + k * T;
+        if (kPacked) {
+          v[k] = rg_lds4(s_val + px * 16);
+        } else {
+          const uint32_t ta = s_stage + px * 12;
+          v[k].x = rg_lds(ta); v[k].y = rg_lds(ta + 4); v[k].z = rg_lds(ta + 8);
+          v[k].w = rg_lds(s_stage + W * 12 + px * 4);
+        }
+        mk[k] = 1.f;
+        if (kHasMask) mk[k] = rg_lds(s_stage + (kRgPerThread * 16) * T + px * 4);
+      }
+      float ol[kRgPerThread], orr[kRgPerThread];
+      uint32_t haddr[kRgPerThread];
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        const int px = tid + k * T;
+        const float d = v[k].w;
+        const float xs = xs0 + (float)k * fT;              // == (float)px + 0.5f exactly
+        const float bu = fmaf(M.y, ys, M.x * xs) + M.z;
+        const float x = fmaf(fmaf(M.w, d, bu), ds, -0.5f);
+        const float rr = d * inv_md;
+        float w = ex2_approx(fmaf(__saturatef(rr), k2, -k2h));
+        w = rr > 0.f ? w : 0.f;
+        if (kHasMask) w *= mk[k];
+        // axis_weights(x, w_t) (render_fast.cuh); floor through one round-down add: for xc in [-2, 2^22) the sum xc + (2^23 + 2)
+        // lies where floats are the integers, so RD gives floor(xc) + 2^23 + 2 exactly -- no F2I / I2F
+        const float xc = fminf(fmaxf(x, -2.f), x_hi);
+        const float rfl = __fadd_rd(xc, 8388610.f);
+        const int i0 = __float_as_int(rfl) - (0x4B000000 + 2);
+        const float x0 = rfl - 8388610.f;
+        const float w1 = x - x0, w0 = (x0 + 1.f) - x;
+        const float aw0 = ((unsigned)i0 < (unsigned)w_t) ? w0 : 0.f;
+        const float aw1 = ((unsigned)(i0 + 1) < (unsigned)w_t) ? w1 : 0.f;
+        ol[k] = thresh(aw0 * wy); orr[k] = thresh(aw1 * wy);
+        v[k].x *= w; v[k].y *= w; v[k].z *= w; v[k].w = w;
+        // i0 in [-1, w_t - 1] whenever a weight survives (NaN-safe: comparisons with garbage are false)
+        const bool on = px < W && (ol[k] + orr[k]) * w > 0.f;
+        haddr[k] = on ? s_head + (i0 + 1) * 4 : s_dummy;
+      }
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        const int px = tid + k * T;
+        rg_sts4(s_val + px * 16, v[k].x, v[k].y, v[k].z, v[k].w);
+        rg_sts(s_wl + px * 4, ol[k]);
+        rg_sts(s_wr + px * 4, orr[k]);
+      }
+      uint32_t old[kRgPerThread];
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) old[k] = rg_exch(haddr[k], tag | (uint32_t)(tid + k * T));
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        const uint32_t o = old[k] ^ tag;
+        rg_sts_u16(s_next + (tid + k * T) * 2, o < 0x10000u ? o : kRgNil);
+      }
+      rg_bar_consumers(T);
+      // ---- pass 2: thread = list; one walk, both target cells
+      uint32_t node[kRgPerThread];
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        const int j = min(tid + k * T, w_t + 1);        // (list w_t + 1 does not exist: a word that never carries a tag)
+        node[k] = rg_lds_u32(s_head + j * 4) ^ tag;
+      }
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        uint32_t n = node[k];
+        while (n < 0x10000u) {
+          const float4 nv = rg_lds4(s_val + n * 16);
+          const float o_l = rg_lds(s_wl + n * 4), o_r = rg_lds(s_wr + n * 4);
+          n = rg_lds_u16(s_next + n * 2);
+          accL[k].x = fmaf(nv.x, o_l, accL[k].x); accL[k].y = fmaf(nv.y, o_l, accL[k].y);
+          accL[k].z = fmaf(nv.z, o_l, accL[k].z); accL[k].w = fmaf(nv.w, o_l, accL[k].w);
+          accR[k].x = fmaf(nv.x, o_r, accR[k].x); accR[k].y = fmaf(nv.y, o_r, accR[k].y);
+          accR[k].z = fmaf(nv.z, o_r, accR[k].z); accR[k].w = fmaf(nv.w, o_r, accR[k].w);
+          if (n == kRgNil) break;
+        }
+      }
+      // the stage (generic-proxy writes when packed) goes back to the copy engine
+      if (kPacked) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (kind & kRgLast) {       // every warp's lane 0 hands its accL (cell j - 1 = the previous warp's last cell) over
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kRgPerThread; ++k)
+          rg_sts4(s_bnd + (k * nwarps + warp) * 16, accL[k].x, accL[k].y, accL[k].z, accL[k].w);
+      }
+    }
+    rg_bar_consumers(T);
+    if (tid == 0) rg_mbar_arrive(sbase + 64 + slot * 8);
+    if (++slot == p.stages) { slot = 0; parity ^= 1; }
+
+    if (kind & kRgLast) {
+      // ---- cell j = accR of thread j + accL of thread j + 1; normalise + store (ldi.py:165-173; normalize_fast_kernel's arithmetic)
+      const size_t out_row = __float_as_uint(d1.z);
+      const bool nan = (kind & kRgNan) != 0;
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) {
+        const int c0 = k * T + warp * 32;           // first cell of this warp's 32
+        if (c0 < w_t) {                             // warp uniform
+          const int c = c0 + lane;
+          float4 nl;
+          nl.x = __shfl_down_sync(0xffffffffu, accL[k].x, 1); nl.y = __shfl_down_sync(0xffffffffu, accL[k].y, 1);
+          nl.z = __shfl_down_sync(0xffffffffu, accL[k].z, 1); nl.w = __shfl_down_sync(0xffffffffu, accL[k].w, 1);
+          if (lane == 31) {                         // next thread = lane 0 of the next warp (same k) or of warp 0 (k + 1)
+            const int nk = warp + 1 < nwarps ? k : k + 1, nw = warp + 1 < nwarps ? warp + 1 : 0;
+            nl = nk < kRgPerThread ? rg_lds4(s_bnd + (nk * nwarps + nw) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const float ax_ = accR[k].x + nl.x, ay_ = accR[k].y + nl.y, az_ = accR[k].z + nl.z;
+          float Wsum = (accR[k].w + nl.w) + p.nb;
+          const float Wi = __frcp_rn(safe_den(Wsum));
+          float r_ = (ax_ + p.nb) * Wi, g_ = (ay_ + p.nb) * Wi, b_ = (az_ + p.nb) * Wi;
+          if (nan) { r_ = g_ = b_ = Wsum = __int_as_float(0x7fc00000); }
+          if (c < w_t) __stcs(p.wts + out_row + c, Wsum);
+          if (vec_out) {
+            rg_sts(s_xpose + lane * 12, r_); rg_sts(s_xpose + lane * 12 + 4, g_); rg_sts(s_xpose + lane * 12 + 8, b_);
+            __syncwarp();
+            const int nf = 3 * min(32, w_t - c0);   // floats of this chunk (multiple of 4: w_t % 4 == 0)
+            if (lane * 4 < nf) __stcs(reinterpret_cast<float4*>(p.img + (out_row + c0) * 3) + lane, rg_lds4(s_xpose + lane * 16));
+            __syncwarp();
+          } else if (c < w_t) {
+            float* ip = p.img + (out_row + c) * 3;
+            __stcs(ip, r_); __stcs(ip + 1, g_); __stcs(ip + 2, b_);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kRgPerThread; ++k) { accL[k] = make_float4(0.f, 0.f, 0.f, 0.f); accR[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      rg_bar_consumers(T);      // s_bnd is rewritten at the next row's end; keep the readers ahead of it
+    }
+  }
+}
+
+}  // namespace lsi

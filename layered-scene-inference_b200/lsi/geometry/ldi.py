@@ -57,9 +57,59 @@ def _px_stride(t, name):
     return t.contiguous(), C
 
 
+class _PoseClassCache(object):
+    """Which camera sets are entirely in the rectified pose class (n == 1, y' independent of x and d: stereo pairs) -- the class
+    the row-gather kernel renders on its own (csrc/render_rowgather.cuh).  The classification itself happens on the device in
+    every call (proj_matrix_kernel writes one flag per image next to the matrices); this cache only remembers the flags of camera
+    tensors it has seen before, so that a later call with the SAME tensor objects at the SAME versions can tell the library
+    (variant 5) not to launch the fallback kernels for other pose classes at all.  Nothing ever synchronises: the flags of a
+    first-seen camera set are copied back asynchronously and used once the copy has completed.  Entries are tied to the tensor
+    objects by weak references (an address alone could be reused by a different tensor) and to their version counters (in-place
+    updates); tensors that keep changing are marked volatile and not looked at again."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def lookup(self, cams):
+        import weakref
+        key = tuple(id(c) for c in cams)
+        vers = tuple(c._version for c in cams)
+        e = self.entries.get(key)
+        if e is not None and not all(r() is c for r, c in zip(e['refs'], cams)):
+            e = None                                   # an id was recycled by another object
+        if e is None:
+            if len(self.entries) > 64:
+                self.entries.clear()
+            e = dict(refs=tuple(weakref.ref(c) for c in cams), vers=vers, state=None, pending=None, volatile=False)
+            self.entries[key] = e
+            return e, False
+        if e['vers'] != vers:                          # modified in place since: classify again, once
+            e['volatile'] = e['state'] is not None or e['pending'] is not None or e['volatile']
+            e.update(vers=vers, state=None, pending=None)
+            return e, False
+        if e['pending'] is not None and e['pending'][1].query():
+            e['state'] = bool(e['pending'][0].all().item())
+            e['pending'] = None
+        return e, e['state'] is True
+
+    @staticmethod
+    def record(e, ws, batch):
+        """Start the asynchronous read-back of this call's per-image class flags (they follow the B 4x4 matrices in the workspace)."""
+        if e is None or e['volatile'] or e['state'] is not None or e['pending'] is not None:
+            return
+        host = torch.empty(batch, dtype=torch.int32, pin_memory=True)
+        host.copy_(ws[batch * 64: batch * 68].view(torch.int32), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        e['pending'] = (host, ev)
+
+
+_POSE_CACHE = _PoseClassCache()
+
+
 class _ForwardSplat(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tex, mask, disp, pc, k_s, k_t, rot, t, focal, cfg):
+    def forward(ctx, tex, mask, disp, pc, k_s, k_t, rot, t, focal, cfg, pose_entry=None):
         L, B, H, W, _ = tex.shape
         h_t, w_t, ds, compose, want_disp, bg, max_disp, scale, variant = cfg
         tex_v, tex_s = _px_stride(tex, 'tex')
@@ -80,6 +130,7 @@ class _ForwardSplat(torch.autograd.Function):
                    _b200.ptr(pc), _b200.ptr(k_s), _b200.ptr(k_t), _b200.ptr(rot), _b200.ptr(t), _b200.ptr(focal),
                    _b200.ptr(img), _b200.ptr(wts), _b200.ptr(dsp), _b200.ptr(layer_acc), _b200.ptr(ws), ws_bytes,
                    _b200.stream())
+        _PoseClassCache.record(pose_entry, ws, B)
         if needs_grad:
             ctx.save_for_backward(tex, mask, disp, pc, k_s, k_t, rot, t, focal, img, wts, layer_acc)
             ctx.cfg = cfg
@@ -109,7 +160,7 @@ class _ForwardSplat(torch.autograd.Function):
                    _b200.ptr(img), _b200.ptr(wts), _b200.ptr(layer_acc), _b200.ptr(g_img), _b200.ptr(g_wts),
                    _b200.ptr(g_disp), _b200.ptr(d_tex), _b200.ptr(d_mask), _b200.ptr(d_disp), _b200.ptr(ws), ws_bytes,
                    _b200.stream())
-        return d_tex, d_mask, d_disp, None, None, None, None, None, None, None
+        return d_tex, d_mask, d_disp, None, None, None, None, None, None, None, None
 
 
 def forward_splat(ldi_src, pixel_coords_src, k_s, k_t, rot, t, focal_disps=None, compose_layers=True,
@@ -142,6 +193,9 @@ def forward_splat(ldi_src, pixel_coords_src, k_s, k_t, rot, t, focal_disps=None,
         if tuple(pc.shape) != (B, H, W, 3):
             raise RuntimeError('lsi_b200: pixel_coords_src must be %s, got %s' % ((B, H, W, 3), tuple(pc.shape)))
     from lsi.geometry import projection
+    pose_entry, all_rect = None, False
+    if _variant == 0 and all(isinstance(c, torch.Tensor) and c.is_cuda for c in (k_s, k_t, rot, t)):
+        pose_entry, all_rect = _POSE_CACHE.lookup((k_s, k_t, rot, t))
     k_s, k_t, rot, t = projection._cam(k_s, k_t, rot, t)
     if k_s.shape[0] != B:
         raise RuntimeError('lsi_b200: camera batch %d != LDI batch %d' % (k_s.shape[0], B))
@@ -155,5 +209,5 @@ def forward_splat(ldi_src, pixel_coords_src, k_s, k_t, rot, t, focal_disps=None,
         raise RuntimeError('lsi_b200: trg_downsampling=%r does not give an integral target size for %dx%d'
                            % (trg_downsampling, H, W))
     cfg = (int(h_t), int(w_t), float(trg_downsampling), bool(compose_layers), bool(compute_trg_disp),
-           float(bg_layer_disp), float(max_disp), float(zbuf_scale), int(_variant))
-    return _ForwardSplat.apply(tex, mask, disp, pc, k_s, k_t, rot, t, focal, cfg)
+           float(bg_layer_disp), float(max_disp), float(zbuf_scale), 5 if all_rect else int(_variant))
+    return _ForwardSplat.apply(tex, mask, disp, pc, k_s, k_t, rot, t, focal, cfg, pose_entry)
