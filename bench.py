@@ -32,7 +32,7 @@ import torch
 H, W, L, B_PER_GPU = 256, 832, 4, 64
 MAX_DISP, BG_DISP, ZBUF_SCALE, DS = 0.4, 1e-3, 50.0, 1.0      # kitti constants, ldi_enc_dec.py:421-425
 METRIC = 'rendered views/sec at 256x832x4-layer'
-SPLAT_TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'r2_splat_traffic.json')   # dram bytes of the splat + normalise launches, from a
+SPLAT_TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'r2_splat_rowgather_traffic.json')   # dram bytes of the splat + normalise launches, from a
                                                                                 # committed ncu capture (--cache-control none); see tools/ncu_summary.py
 WORKLOAD = ('KITTI-like 256x832 image -> encoder-decoder U-Net + 4 LDI heads (W zero-padded to 896 for the U-Net, '
             'prediction cropped; tcgen05 convs in the fp32-parity split-precision mode, batch-stat BN) -> forward_splat(compose_layers=True, '
@@ -321,10 +321,13 @@ def main():
         with open(SPLAT_TRAFFIC_FILE) as f:
             tj = json.load(f)
         traffic = tj['dram_bytes_per_view'] * B / n_launch
-    roofline = {'bound': 'hbm', 'kernel': 'splat_fwd_stream_kernel + normalize_fast_kernel (forward splat into the L2-resident accumulator, then '
-                                          'bg / divide_safe / store; %d launches of each per step)' % n_launch,
+    fused = kn[1] == 0      # row-gather kernel: splat + normalise in one launch (rectified poses); else the reduction kernels + normalise pass
+    roofline = {'bound': 'hbm', 'kernel': ('splat_fwd_rowgather_kernel (target rows owned by CTAs, scatter inverted in shared memory, bg / divide_safe / '
+                                           'store fused; %d launch per step)' % n_launch) if fused else
+                                          ('splat_fwd_stream_kernel + normalize_fast_kernel (forward splat into the L2-resident accumulator, then '
+                                           'bg / divide_safe / store; %d launches of each per step)' % n_launch),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
-                'traffic': traffic, 'traffic_source': 'profiles/r2_splat_traffic.json (ncu dram__bytes_read+write, --cache-control none)' if traffic else None,
+                'traffic': traffic, 'traffic_source': 'profiles/r2_splat_rowgather_traffic.json (ncu dram__bytes_read+write, --cache-control none)' if traffic else None,
                 'algorithmic_bytes_per_launch': bytes_step / n_launch, 'algorithmic_bytes_per_step': bytes_step,
                 'definition': 'SURVEY 8(d) bytes_fwd, packed (mask==1, no trg_disp): 4*(4*L*N + 4*N_t) per view, over splat + normalise time',
                 'kernel_ms_per_step': splat_ms + norm_ms, 'splat_ms_per_step': splat_ms, 'normalize_ms_per_step': norm_ms,

@@ -492,8 +492,7 @@ static int launch_rowgather(const lsi_b200_splat_desc* d, const float* tex, cons
   p.off_next = (int)off; off = align_up(off + wpad * 2, 16);
   p.off_wl = (int)off; off = align_up(off + wpad * 4, 16);
   p.off_wr = (int)off; off = align_up(off + wpad * 4, 16);
-  p.off_xpose = (int)off; off += (size_t)(threads / 32) * 384;
-  p.off_bnd = (int)off; off += (size_t)kRgPerThread * (threads / 32) * 16;
+  p.off_bnd = (int)off; off += ((size_t)kRgPerThread * (threads / 32) + 1) * 16;
   p.off_val4 = (int)off; if (!packed) off += wpad * 16;
   off = align_up(off, 128);
   p.off_ring = (int)off;

@@ -19,8 +19,7 @@
 //         loops).  List heads carry a 16-bit generation tag, so they are never cleared between items;
 //       pass 2 (thread = target cell): walks the list of its own cell (left weights) and of its left neighbour's cell
 //         (right weights) and accumulates in REGISTERS -- a gather, no float atomics anywhere;
-//   * after the last item of a row the thread normalises (ldi.py:165-173, bg canvas folded in) and stores its cells once,
-//     through a warp-private transposition buffer so that the stores are 128-bit.
+//   * after the last item of a row the thread normalises (ldi.py:165-173, bg canvas folded in) and stores its cells once.
 //
 // HBM traffic = the algorithmic bytes (every source row read once when it maps to one target row, otherwise again through
 // L2; every target pixel written once); no accumulator, no memset, no normalise launch.  Same per-pixel formulas as
@@ -47,7 +46,7 @@ struct RowGatherParams {
   float ds, inv_max_disp, k2, k2h, nb;
   int threads;              // consumer threads (multiple of 32); the producer warp follows them
   int stages, stage_bytes;
-  int off_desc, off_val4, off_wl, off_wr, off_head, off_next, off_xpose, off_bnd, off_ring;   // shared-memory layout (bytes)
+  int off_desc, off_val4, off_wl, off_wr, off_head, off_next, off_bnd, off_ring;   // shared-memory layout (bytes)
   long long tasks;          // B * l_outer * h_t
 };
 
@@ -192,6 +191,7 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = tid; c < p.w_t + 34; c += blockDim.x) rg_sts_u32(sbase + p.off_head + c * 4, 0u);      // w_t + 1 lists, a never-tagged word, 32 dummies
+  if (tid == 0) rg_sts4(sbase + p.off_bnd + kRgPerThread * (p.threads >> 5) * 16, 0.f, 0.f, 0.f, 0.f);   // see the row epilogue
   __syncthreads();
   const long long t0 = p.tasks * blockIdx.x / gridDim.x, t1 = p.tasks * (blockIdx.x + 1) / gridDim.x;
 
@@ -203,12 +203,11 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
   // ---- consumers
   const int w_t_ = p.w_t;
   const uint32_t s_wl = sbase + p.off_wl, s_wr = sbase + p.off_wr, s_head = sbase + p.off_head, s_next = sbase + p.off_next;
-  const uint32_t s_xpose = sbase + p.off_xpose + warp * 384, s_bnd = sbase + p.off_bnd;
+  const uint32_t s_bnd = sbase + p.off_bnd;
   const uint32_t s_dummy = s_head + (w_t_ + 2 + lane) * 4;      // per-lane dummy list head (words w_t + 2 ... w_t + 33)
   const int W = p.W, w_t = p.w_t, nwarps = T >> 5;
   const float ds = p.ds, inv_md = p.inv_max_disp, k2 = p.k2, k2h = p.k2h;
   const float x_hi = (float)w_t + 1.f, xs0 = (float)tid + 0.5f, fT = (float)T;
-  const bool vec_out = (w_t & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.img) & 15) == 0);
   // thread j walks list j (source pixels whose left cell is j - 1, right cell j): accL -> cell j - 1, accR -> cell j (its own)
   float4 accL[kRgPerThread], accR[kRgPerThread];
 #pragma unroll
@@ -334,9 +333,12 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
     if (++slot == p.stages) { slot = 0; parity ^= 1; }
 
     if (kind & kRgLast) {
-      // ---- cell j = accR of thread j + accL of thread j + 1; normalise + store (ldi.py:165-173; normalize_fast_kernel's arithmetic)
-      const size_t out_row = __float_as_uint(d1.z);
-      const bool nan = (kind & kRgNan) != 0;
+      // ---- cell j = accR of thread j + accL of thread j + 1; normalise + store (ldi.py:165-173: (sum + bg) / divide_safe(sum_w + bg);
+      // the reciprocal is rcp.approx, <= 1 ulp from the correctly rounded one normalize_fast_kernel takes)
+      const uint32_t out_row = __float_as_uint(d1.z);
+      float* const wts_p = p.wts + out_row;
+      float* const img_p = p.img + (size_t)out_row * 3;
+      const float nbv = (kind & kRgNan) ? __int_as_float(0x7fc00000) : p.nb;      // an image outside the class under the all-rectified hint: NaNs
 #pragma unroll
       for (int k = 0; k < kRgPerThread; ++k) {
         const int c0 = k * T + warp * 32;           // first cell of this warp's 32
@@ -345,24 +347,17 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
           float4 nl;
           nl.x = __shfl_down_sync(0xffffffffu, accL[k].x, 1); nl.y = __shfl_down_sync(0xffffffffu, accL[k].y, 1);
           nl.z = __shfl_down_sync(0xffffffffu, accL[k].z, 1); nl.w = __shfl_down_sync(0xffffffffu, accL[k].w, 1);
-          if (lane == 31) {                         // next thread = lane 0 of the next warp (same k) or of warp 0 (k + 1)
-            const int nk = warp + 1 < nwarps ? k : k + 1, nw = warp + 1 < nwarps ? warp + 1 : 0;
-            nl = nk < kRgPerThread ? rg_lds4(s_bnd + (nk * nwarps + nw) * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          const float ax_ = accR[k].x + nl.x, ay_ = accR[k].y + nl.y, az_ = accR[k].z + nl.z;
-          float Wsum = (accR[k].w + nl.w) + p.nb;
-          const float Wi = __frcp_rn(safe_den(Wsum));
-          float r_ = (ax_ + p.nb) * Wi, g_ = (ay_ + p.nb) * Wi, b_ = (az_ + p.nb) * Wi;
-          if (nan) { r_ = g_ = b_ = Wsum = __int_as_float(0x7fc00000); }
-          if (c < w_t) __stcs(p.wts + out_row + c, Wsum);
-          if (vec_out) {
-            rg_sts(s_xpose + lane * 12, r_); rg_sts(s_xpose + lane * 12 + 4, g_); rg_sts(s_xpose + lane * 12 + 8, b_);
-            __syncwarp();
-            const int nf = 3 * min(32, w_t - c0);   // floats of this chunk (multiple of 4: w_t % 4 == 0)
-            if (lane * 4 < nf) __stcs(reinterpret_cast<float4*>(p.img + (out_row + c0) * 3) + lane, rg_lds4(s_xpose + lane * 16));
-            __syncwarp();
-          } else if (c < w_t) {
-            float* ip = p.img + (out_row + c) * 3;
+          // lane 31's right neighbour is lane 0 of the next warp (same k) or of warp 0 (k + 1): entry k * nwarps + warp + 1 either way
+          // (the entry past the last one stays zero)
+          if (lane == 31) nl = rg_lds4(s_bnd + (k * nwarps + warp + 1) * 16);
+          const float Wsum = (accR[k].w + nl.w) + nbv;
+          float Wi;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(Wi) : "f"(safe_den(Wsum)));
+          const float r_ = ((accR[k].x + nl.x) + nbv) * Wi, g_ = ((accR[k].y + nl.y) + nbv) * Wi, b_ = ((accR[k].z + nl.z) + nbv) * Wi;
+          if (c < w_t) {
+            // three scalar stores per cell: a 128-bit variant through a shared-memory transposition measured slower (0.33 vs 0.32 ms)
+            __stcs(wts_p + c, Wsum);
+            float* ip = img_p + c * 3;
             __stcs(ip, r_); __stcs(ip + 1, g_); __stcs(ip + 2, b_);
           }
         }
