@@ -487,7 +487,7 @@ static int launch_rowgather(const lsi_b200_splat_desc* d, const float* tex, cons
   const bool small = threads + 32 <= 256;
   size_t off = 128;                                         // full / empty mbarriers (<= 8 stages)
   p.off_desc = (int)off; off += 8 * 32;                     // item descriptors
-  const size_t wpad = (size_t)kRgPerThread * threads;       // every per-pixel array is padded to 4 entries per consumer thread
+  const size_t wpad = (size_t)kRgPerThread * (threads + (packed ? 0 : 2));       // every per-node array: 4 entries per consumer thread (node stride threads + 2 for planar rows)
   p.off_head = (int)off; off = align_up(off + ((size_t)d->w_t + 34) * 4, 16);
   p.off_next = (int)off; off = align_up(off + wpad * 2, 16);
   p.off_wl = (int)off; off = align_up(off + wpad * 4, 16);
@@ -508,19 +508,20 @@ static int launch_rowgather(const lsi_b200_splat_desc* d, const float* tex, cons
   if (per_sm > want_ctas) per_sm = want_ctas;
   long long grid = (long long)sms * per_sm;
   if (grid > p.tasks) grid = p.tasks;
-  const int ki = (small ? 0 : 4) | (mask ? 2 : 0) | (packed ? 1 : 0);
+  // instantiations: consumer threads as a compile-time constant for the two BASELINE widths (832 -> 224, 1664 -> 448), run-time otherwise
+  const int tsel = threads == 224 ? 0 : threads == 448 ? 2 : small ? 1 : 3;
+  const int ki = tsel * 4 + ((mask ? 2 : 0) | (packed ? 1 : 0));
   void (*kern)(const RowGatherParams) = nullptr;
+#define LSI_RG_CASE(i, cta, kt, m, pk) case i: kern = splat_fwd_rowgather_kernel<cta, kt, m, pk>; break;
   switch (ki) {
-    case 0: kern = splat_fwd_rowgather_kernel<256, false, false>; break;
-    case 1: kern = splat_fwd_rowgather_kernel<256, false, true>; break;
-    case 2: kern = splat_fwd_rowgather_kernel<256, true, false>; break;
-    case 3: kern = splat_fwd_rowgather_kernel<256, true, true>; break;
-    case 4: kern = splat_fwd_rowgather_kernel<544, false, false>; break;
-    case 5: kern = splat_fwd_rowgather_kernel<544, false, true>; break;
-    case 6: kern = splat_fwd_rowgather_kernel<544, true, false>; break;
-    default: kern = splat_fwd_rowgather_kernel<544, true, true>; break;
+    LSI_RG_CASE(0, 256, 224, false, false) LSI_RG_CASE(1, 256, 224, false, true) LSI_RG_CASE(2, 256, 224, true, false) LSI_RG_CASE(3, 256, 224, true, true)
+    LSI_RG_CASE(4, 256, 0, false, false) LSI_RG_CASE(5, 256, 0, false, true) LSI_RG_CASE(6, 256, 0, true, false) LSI_RG_CASE(7, 256, 0, true, true)
+    LSI_RG_CASE(8, 544, 448, false, false) LSI_RG_CASE(9, 544, 448, false, true) LSI_RG_CASE(10, 544, 448, true, false) LSI_RG_CASE(11, 544, 448, true, true)
+    LSI_RG_CASE(12, 544, 0, false, false) LSI_RG_CASE(13, 544, 0, false, true) LSI_RG_CASE(14, 544, 0, true, false)
+    default: kern = splat_fwd_rowgather_kernel<544, 0, true, true>; break;
   }
-  static size_t smem_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#undef LSI_RG_CASE
+  static size_t smem_set[16] = {0};
   if (smem > smem_set[ki]) {
     LSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set[ki] = smem;

@@ -59,6 +59,12 @@ __device__ __forceinline__ uint32_t rg_lds_u16(uint32_t a) {
 __device__ __forceinline__ float4 rg_lds4(uint32_t a) {
   float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
 }
+__device__ __forceinline__ float2 rg_lds2(uint32_t a) {
+  float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ void rg_sts2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
 __device__ __forceinline__ void rg_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void rg_sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void rg_sts4(uint32_t a, float x, float y, float z, float w) {
@@ -176,12 +182,14 @@ __device__ __forceinline__ void rg_producer(const RowGatherParams& p, uint32_t s
 }
 
 // kCtaThreads = consumer threads + the producer warp: 256 (rows up to 896 pixels, 4 CTAs per SM) or 544 (up to 2048, 2 per SM)
-template <int kCtaThreads, bool kHasMask, bool kPacked>
+// kT: consumer threads as a compile-time constant (224: rows of up to 895 pixels -- the headline 832; 448: up to 1791 -- config 5) so
+// that every per-pixel address is base + immediate; 0 = run-time p.threads (any other width up to 2048)
+template <int kCtaThreads, int kT, bool kHasMask, bool kPacked>
 __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_CTAS : 1) splat_fwd_rowgather_kernel(const RowGatherParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = st_smem_u32(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = p.threads;
+  const int T = kT ? kT : p.threads;
   // [0,64): full barriers, [64,128): empty barriers
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -202,12 +210,20 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
 
   // ---- consumers
   const int w_t_ = p.w_t;
-  const uint32_t s_wl = sbase + p.off_wl, s_wr = sbase + p.off_wr, s_head = sbase + p.off_head, s_next = sbase + p.off_next;
+  const uint32_t s_w2 = sbase + p.off_wl, s_head = sbase + p.off_head, s_next = sbase + p.off_next;
   const uint32_t s_bnd = sbase + p.off_bnd;
   const uint32_t s_dummy = s_head + (w_t_ + 2 + lane) * 4;      // per-lane dummy list head (words w_t + 2 ... w_t + 33)
   const int W = p.W, w_t = p.w_t, nwarps = T >> 5;
   const float ds = p.ds, inv_md = p.inv_max_disp, k2 = p.k2, k2h = p.k2h;
-  const float x_hi = (float)w_t + 1.f, xs0 = (float)tid + 0.5f, fT = (float)T;
+  // pass 1 pixel <-> thread: packed rows: pixel tid + k*T (conflict-free 128-bit loads); planar rows: the four consecutive pixels
+  // 4*tid + k (three 128-bit loads for their 12 texture floats, one for the disparities).  Either way pixel k of thread tid becomes
+  // list node tid + k*T: the lists do not care which pixel a node is.
+  const float x_hi = (float)w_t + 1.f, xs0 = (float)(kPacked ? tid : 4 * tid) + 0.5f, xs_step = kPacked ? (float)T : 1.f;
+  const int px0 = kPacked ? tid : 4 * tid, px_step = kPacked ? T : 1;
+  // node stride: planar rows put a thread's four consecutive pixels T + 2 nodes apart -- with T (a multiple of 32) the four pixels of
+  // a quad would share a bank group and pass 2, which reads ~consecutive PIXELS, would see 4-way conflicts on its 128-bit loads
+  const int NS = kPacked ? T : T + 2;
+  const uint32_t a_w2 = s_w2 + tid * 8, a_next = s_next + tid * 2;          // node tid's slots; node tid + k*T: + k*T*8 / + k*T*2
   // thread j walks list j (source pixels whose left cell is j - 1, right cell j): accL -> cell j - 1, accR -> cell j (its own)
   float4 accL[kRgPerThread], accR[kRgPerThread];
 #pragma unroll
@@ -238,28 +254,31 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
       // on whatever the slot holds and store into their own padding; their list insertion goes to a per-lane dummy head.
       // Written in phases over the thread's four pixels (loads / arithmetic / stores / exchanges / links): the shared-memory
       // accesses are ordered asm statements, so this is what lets four independent chains overlap.
+      const uint32_t a_val = s_val + tid * 16;
       float4 v[kRgPerThread];
       float mk[kRgPerThread];
+      if (kPacked) {
 #pragma unroll
-      for (int k = 0; k < kRgPerThread; ++k) {
-        const int px = tid + k * T;
-        if (kPacked) {
-          v[k] = rg_lds4(s_val + px * 16);
-        } else {
-          const uint32_t ta = s_stage + px * 12;
-          v[k].x = rg_lds(ta); v[k].y = rg_lds(ta + 4); v[k].z = rg_lds(ta + 8);
-          v[k].w = rg_lds(s_stage + W * 12 + px * 4);
+        for (int k = 0; k < kRgPerThread; ++k) v[k] = rg_lds4(a_val + k * NS * 16);
+#pragma unroll
+        for (int k = 0; k < kRgPerThread; ++k) mk[k] = kHasMask ? rg_lds(s_stage + (kRgPerThread * 16) * T + (tid + k * T) * 4) : 1.f;
+      } else {
+        const float4 t0 = rg_lds4(s_stage + tid * 48), t1 = rg_lds4(s_stage + tid * 48 + 16), t2 = rg_lds4(s_stage + tid * 48 + 32);
+        const float4 dd = rg_lds4(s_stage + W * 12 + tid * 16);
+        v[0] = make_float4(t0.x, t0.y, t0.z, dd.x); v[1] = make_float4(t0.w, t1.x, t1.y, dd.y);
+        v[2] = make_float4(t1.z, t1.w, t2.x, dd.z); v[3] = make_float4(t2.y, t2.z, t2.w, dd.w);
+        mk[0] = mk[1] = mk[2] = mk[3] = 1.f;
+        if (kHasMask) {
+          const float4 mm = rg_lds4(s_stage + (kRgPerThread * 16) * T + tid * 16);
+          mk[0] = mm.x; mk[1] = mm.y; mk[2] = mm.z; mk[3] = mm.w;
         }
-        mk[k] = 1.f;
-        if (kHasMask) mk[k] = rg_lds(s_stage + (kRgPerThread * 16) * T + px * 4);
       }
       float ol[kRgPerThread], orr[kRgPerThread];
       uint32_t haddr[kRgPerThread];
 #pragma unroll
       for (int k = 0; k < kRgPerThread; ++k) {
-        const int px = tid + k * T;
         const float d = v[k].w;
-        const float xs = xs0 + (float)k * fT;              // == (float)px + 0.5f exactly
+        const float xs = xs0 + (float)k * xs_step;         // == (float)px + 0.5f exactly
         const float bu = fmaf(M.y, ys, M.x * xs) + M.z;
         const float x = fmaf(fmaf(M.w, d, bu), ds, -0.5f);
         const float rr = d * inv_md;
@@ -278,23 +297,21 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
         ol[k] = thresh(aw0 * wy); orr[k] = thresh(aw1 * wy);
         v[k].x *= w; v[k].y *= w; v[k].z *= w; v[k].w = w;
         // i0 in [-1, w_t - 1] whenever a weight survives (NaN-safe: comparisons with garbage are false)
-        const bool on = px < W && (ol[k] + orr[k]) * w > 0.f;
+        const bool on = px0 + k * px_step < W && (ol[k] + orr[k]) * w > 0.f;
         haddr[k] = on ? s_head + (i0 + 1) * 4 : s_dummy;
       }
 #pragma unroll
       for (int k = 0; k < kRgPerThread; ++k) {
-        const int px = tid + k * T;
-        rg_sts4(s_val + px * 16, v[k].x, v[k].y, v[k].z, v[k].w);
-        rg_sts(s_wl + px * 4, ol[k]);
-        rg_sts(s_wr + px * 4, orr[k]);
+        rg_sts4(a_val + k * NS * 16, v[k].x, v[k].y, v[k].z, v[k].w);
+        rg_sts2(a_w2 + k * NS * 8, ol[k], orr[k]);
       }
       uint32_t old[kRgPerThread];
 #pragma unroll
-      for (int k = 0; k < kRgPerThread; ++k) old[k] = rg_exch(haddr[k], tag | (uint32_t)(tid + k * T));
+      for (int k = 0; k < kRgPerThread; ++k) old[k] = rg_exch(haddr[k], tag | (uint32_t)(tid + k * NS));
 #pragma unroll
       for (int k = 0; k < kRgPerThread; ++k) {
         const uint32_t o = old[k] ^ tag;
-        rg_sts_u16(s_next + (tid + k * T) * 2, o < 0x10000u ? o : kRgNil);
+        rg_sts_u16(a_next + k * NS * 2, o < 0x10000u ? o : kRgNil);
       }
       rg_bar_consumers(T);
       // ---- pass 2: thread = list; one walk, both target cells
@@ -309,7 +326,8 @@ __global__ void __launch_bounds__(kCtaThreads, kCtaThreads <= 256 ? LSI_RG_MIN_C
         uint32_t n = node[k];
         while (n < 0x10000u) {
           const float4 nv = rg_lds4(s_val + n * 16);
-          const float o_l = rg_lds(s_wl + n * 4), o_r = rg_lds(s_wr + n * 4);
+          const float2 o2 = rg_lds2(s_w2 + n * 8);
+          const float o_l = o2.x, o_r = o2.y;
           n = rg_lds_u16(s_next + n * 2);
           accL[k].x = fmaf(nv.x, o_l, accL[k].x); accL[k].y = fmaf(nv.y, o_l, accL[k].y);
           accL[k].z = fmaf(nv.z, o_l, accL[k].z); accL[k].w = fmaf(nv.w, o_l, accL[k].w);
