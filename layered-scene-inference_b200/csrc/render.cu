@@ -673,7 +673,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
       f.ablate = (d->variant >= 100) ? d->variant - 100 : 0;
       f.skip = skip;
       dim3 fgrid((d->w_s + 63) / 64, d->h_s, bc), fblock(64);
-      if (use_stream) {
+      if (use_stream && !skip) {      // (the streaming kernel has no per-image skip: with some images already rendered, the block kernel)
         if (int rc = launch_stream(f, mask != nullptr, packed, st)) return rc;
       } else {
         ScopedTiming tm(kSplatFwd, st);

@@ -204,7 +204,11 @@ class HostViewPipeline(object):
                 ldi = predict_ldi(x, self.opts, self.store, reuse=True)
                 c = self.cams[s]
                 c['t'].record_stream(cur)
-                img, wts = self._render(tuple(ldi), self.pc, c['k_s'], c['k_t'], c['rot'], c['t'], **self.kw)[:2]
+                # the cameras are re-uploaded every step: identify the set by the content of the host copies, so that the renderer's
+                # pose-class memo (lsi/geometry/ldi.py) can recognise a rectified batch it has classified before
+                hb = batches[k]
+                pose_key = hash(tuple(hb[q].numpy().tobytes() for q in ('k_s', 'k_t', 'rot', 't')))
+                img, wts = self._render(tuple(ldi), self.pc, c['k_s'], c['k_t'], c['rot'], c['t'], _pose_key=pose_key, **self.kw)[:2]
             ev = torch.cuda.Event()
             ev.record(cur)
             free_in[s] = ev
