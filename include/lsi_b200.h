@@ -67,7 +67,10 @@ typedef struct lsi_b200_splat_desc {
   int variant;                                 /* 0 = default; 1 = plain global-atomic kernel (ablation);   */
                                                /* 2 = deterministic row-owner kernel for rectified poses;    */
                                                /* 3 = block-per-segment reduction kernel without the bulk-   */
-                                               /* copy ring (the default before the streaming kernel)        */
+                                               /* copy ring (the default before the streaming kernel);       */
+                                               /* 5 / 6 = default path + a hint from the caller, who has read */
+                                               /* this call's per-image pose-class flags back before: 5 = all */
+                                               /* images are rectified (row-gather kernel only), 6 = none is  */
 } lsi_b200_splat_desc;
 
 /* src->trg (inverse==0, projection.py:71-86) or trg->src (inverse!=0, projection.py:89-106) 4x4 matrices.

@@ -61,8 +61,11 @@ __global__ void proj_matrix_kernel(const float* __restrict__ k_s, const float* _
   }
   o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
   // rectified pose class (row-owner kernel): n == 1, y' independent of x and d, rows keep their order
-  if (rect_flags)
-    rect_flags[b] = (o[8] == 0.f && o[9] == 0.f && o[10] == 1.f && o[11] == 0.f && o[4] == 0.f && o[7] == 0.f && o[5] > 0.f) ? 1 : 0;
+  if (rect_flags) {      // rect_flags[batch] counts the flagged images (zeroed by the caller)
+    const int f = (o[8] == 0.f && o[9] == 0.f && o[10] == 1.f && o[11] == 0.f && o[4] == 0.f && o[7] == 0.f && o[5] > 0.f) ? 1 : 0;
+    rect_flags[b] = f;
+    if (f) atomicAdd(rect_flags + batch, 1);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -343,7 +346,7 @@ static FwdPlan plan_forward(const lsi_b200_splat_desc* d) {
   // guard band on both sides of the chunk accumulator: the streaming kernel adds exact zeros to the (clamped) cell of a
   // pixel that projects outside the image instead of branching around the reduction (render_stream.cuh)
   const size_t guard = align_up(((size_t)4 * d->w_t + 8) * 16, 256);
-  pl.off_acc4 = align_up((size_t)d->batch * 17 * sizeof(float), 256) + guard;   // matrices + rectified-class flags
+  pl.off_acc4 = align_up(((size_t)d->batch * 17 + 1) * sizeof(float), 256) + guard;   // matrices + rectified-class flags + their count
   pl.off_accd = pl.off_acc4 + align_up(n_trg * 16 * pl.nl_acc * bc, 256) + guard;
   pl.total = pl.off_accd + (d->compute_trg_disp ? align_up(n_trg * 8 * d->n_layers * bc, 256) : 0);
   return pl;
@@ -576,6 +579,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   char* ws = static_cast<char*>(workspace);
   float* mats = reinterpret_cast<float*>(ws + pl.off_mats);
   int* rect_flags = reinterpret_cast<int*>(mats + (size_t)d->batch * 16);
+  LSI_CUDA(cudaMemsetAsync(rect_flags + d->batch, 0, sizeof(int), st));
   proj_matrix_kernel<<<(d->batch + 63) / 64, 64, 0, st>>>(k_s, k_t, rot, t, d->batch, 0, mats, rect_flags);
   LSI_LAUNCH_CHECK();
 
@@ -589,7 +593,7 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   // fast path: standard grid, no focal shift, no trg_disp, 16-byte aligned rows, planar (3/1/1) or packed (4/4) layout
   const bool packed = d->tex_px_stride == 4 && d->disp_px_stride == 4 && disp == tex + 3;
   const bool planar = d->tex_px_stride == 3 && d->disp_px_stride == 1;
-  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant == 3 || d->variant == 5 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
+  const bool fast = (d->variant == 0 || d->variant == 2 || d->variant == 3 || d->variant == 5 || d->variant == 6 || d->variant >= 100) && !pixel_coords && !focal_disps && !has_disp && (packed || planar) &&
                     (!mask || d->mask_px_stride == 1) && (!packed || ((uintptr_t)tex & 15) == 0) && d->h_s <= 65535 &&
                     bc_fits_grid;
   // rectified-stereo pose class: warp-owned target rows in shared memory, written once (render_rowowner.cuh); images of
@@ -600,11 +604,11 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
   const bool use_stream_shape = fast && ((uintptr_t)tex & 15) == 0 &&
                       (packed || (d->w_s % 4 == 0 && ((uintptr_t)disp & 15) == 0)) &&
                       (!mask || (d->w_s % 4 == 0 && ((uintptr_t)mask & 15) == 0));
-  const bool use_stream = use_stream_shape && (d->variant == 0 || d->variant == 5) && !rowowner_enabled() && stream_enabled();
+  const bool use_stream = use_stream_shape && (d->variant == 0 || d->variant == 5 || d->variant == 6) && !rowowner_enabled() && stream_enabled();
   // rectified pose class, default: row-gather kernel (render_rowgather.cuh) -- target rows owned by CTAs, the scatter inverted
   // in shared memory, normalisation fused.  variant 5 = the caller knows (from these flags, read back earlier for the same
   // camera tensors) that every image is in the class: the reduction kernels below are not launched at all (a hint: shapes the
-  // kernel does not take run the default path).
+  // kernel does not take run the default path); variant 6 = the caller knows that NO image is in the class: no row-gather launch.
   const bool gather_ok = use_stream_shape && (d->variant == 0 || d->variant == 5) && rowgather_enabled() && !rowowner_enabled();
   if (gather_ok) {
     bool launched = false;
@@ -671,9 +675,9 @@ extern "C" int lsi_b200_forward_splat(const lsi_b200_splat_desc* d, const float*
       f.ds = d->trg_downsampling; f.inv_max_disp = 1.f / d->max_disp;
       f.k2 = d->zbuf_scale * 1.4426950408889634f; f.k2h = 0.5f * f.k2;
       f.ablate = (d->variant >= 100) ? d->variant - 100 : 0;
-      f.skip = skip;
+      f.skip = skip; f.n_flagged = skip ? rect_flags + d->batch : nullptr;
       dim3 fgrid((d->w_s + 63) / 64, d->h_s, bc), fblock(64);
-      if (use_stream && !skip) {      // (the streaming kernel has no per-image skip: with some images already rendered, the block kernel)
+      if (use_stream) {
         if (int rc = launch_stream(f, mask != nullptr, packed, st)) return rc;
       } else {
         ScopedTiming tm(kSplatFwd, st);

@@ -26,7 +26,8 @@ struct FastParams {
   float ds, inv_max_disp;
   float k2, k2h;            // zb = ex2(clip(r)*k2 - k2h), k2 = scale*log2(e), k2h = 0.5*k2
   int ablate;               // measurement only: 1 = no reductions issued, 2 = reductions to the pixel's own cell
-  const int* skip;          // per batch element: 1 = already rendered by the row-owner kernel (nullable)
+  const int* skip;          // per batch element: 1 = already rendered by the row-owner / row-gather kernel (nullable)
+  const int* n_flagged;     // number of such images in the whole batch (with skip)
 };
 
 struct AxisW {   // one axis of the bilinear footprint: integer base, the two weights (validity folded in)

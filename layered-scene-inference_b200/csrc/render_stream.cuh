@@ -314,6 +314,7 @@ template <bool kHasMask, bool kPacked>
 __global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) splat_fwd_stream_kernel(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const FastParams& f = p.f;
+  if (f.skip && *f.n_flagged == f.B) return;   // every image was rendered by the row-gather kernel (render_rowgather.cuh)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // barriers first (8 B each), then the rings
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * p.stages;
@@ -350,12 +351,14 @@ __global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) splat_fwd
   const size_t acc_lstride = f.acc_per_layer ? (size_t)f.bc * n_trg : 0;
   RowConst rc;
   int row_b = -1, row_i = -1;
+  bool row_skip = false;
   int slot = 0;
   uint32_t parity = 0;
   for (int it = 0; it < items; ++it) {
     if (cc.bl != row_b || cc.i != row_i) {
       row_b = cc.bl; row_i = cc.i;
       row_setup(f, f.b0 + cc.bl, cc.i, rc);
+      row_skip = f.skip && f.skip[f.b0 + cc.bl];   // rendered elsewhere: its stages are streamed (mixed batches are rare) but not processed
     }
     unsigned char* stage = ring + (size_t)slot * p.stage_bytes;
     st_mbar_wait(bars + slot, parity);
@@ -363,7 +366,10 @@ __global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm) splat_fwd
     const int j0 = cc.s * kSegPx;
     float4* base0 = f.acc4 + (size_t)cc.bl * n_trg + (size_t)(cc.g * 4) * acc_lstride;
     const bool refill = issued < items;
-    if (rc.mode == 2) {
+    if (row_skip) {
+      __syncwarp();
+      if (refill && st_elect_one()) stream_issue<kHasMask, kPacked>(p, pc, stage, bars + slot, policy);
+    } else if (rc.mode == 2) {
       if (rc.two_rows) stage_run<2, true, kHasMask, kPacked>(p, rc, stage, cc.i, j0, base0, acc_lstride, nl, lane, refill, pc, bars + slot, policy);
       else stage_run<2, false, kHasMask, kPacked>(p, rc, stage, cc.i, j0, base0, acc_lstride, nl, lane, refill, pc, bars + slot, policy);
     } else if (rc.mode == 1) {

@@ -82,15 +82,20 @@ class _PoseClassCache(object):
                 self.entries.clear()
             e = dict(refs=tuple(weakref.ref(c) for c in cams), vers=vers, state=None, pending=None, volatile=False)
             self.entries[key] = e
-            return e, False
+            return e, None
         if e['vers'] != vers:                          # modified in place since: classify again, once
             e['volatile'] = e['state'] is not None or e['pending'] is not None or e['volatile']
             e.update(vers=vers, state=None, pending=None)
-            return e, False
+            return e, None
+        self._resolve(e)
+        return e, e['state']
+
+    @staticmethod
+    def _resolve(e):
         if e['pending'] is not None and e['pending'][1].query():
-            e['state'] = bool(e['pending'][0].all().item())
+            flags = e['pending'][0]
+            e['state'] = 'all' if bool(flags.all().item()) else ('none' if not bool(flags.any().item()) else 'mixed')
             e['pending'] = None
-        return e, e['state'] is True
 
     def lookup_key(self, key):
         """The same memo for callers that identify a camera set by content (e.g. a hash of the host copies they upload every step)
@@ -101,11 +106,9 @@ class _PoseClassCache(object):
                 self.entries.clear()
             e = dict(refs=(), vers=(), state=None, pending=None, volatile=False)
             self.entries[key] = e
-            return e, False
-        if e['pending'] is not None and e['pending'][1].query():
-            e['state'] = bool(e['pending'][0].all().item())
-            e['pending'] = None
-        return e, e['state'] is True
+            return e, None
+        self._resolve(e)
+        return e, e['state']
 
     @staticmethod
     def record(e, ws, batch):
@@ -208,7 +211,7 @@ def forward_splat(ldi_src, pixel_coords_src, k_s, k_t, rot, t, focal_disps=None,
         if tuple(pc.shape) != (B, H, W, 3):
             raise RuntimeError('lsi_b200: pixel_coords_src must be %s, got %s' % ((B, H, W, 3), tuple(pc.shape)))
     from lsi.geometry import projection
-    pose_entry, all_rect = None, False
+    pose_entry, all_rect = None, None
     if _variant == 0 and _pose_key is not None:
         pose_entry, all_rect = _POSE_CACHE.lookup_key(('key', _pose_key))
     elif _variant == 0 and all(isinstance(c, torch.Tensor) and c.is_cuda for c in (k_s, k_t, rot, t)):
@@ -226,5 +229,5 @@ def forward_splat(ldi_src, pixel_coords_src, k_s, k_t, rot, t, focal_disps=None,
         raise RuntimeError('lsi_b200: trg_downsampling=%r does not give an integral target size for %dx%d'
                            % (trg_downsampling, H, W))
     cfg = (int(h_t), int(w_t), float(trg_downsampling), bool(compose_layers), bool(compute_trg_disp),
-           float(bg_layer_disp), float(max_disp), float(zbuf_scale), 5 if all_rect else int(_variant))
+           float(bg_layer_disp), float(max_disp), float(zbuf_scale), {'all': 5, 'none': 6}.get(all_rect, int(_variant)))
     return _ForwardSplat.apply(tex, mask, disp, pc, k_s, k_t, rot, t, focal, cfg, pose_entry)

@@ -115,21 +115,39 @@ def test_rowgather_mixed_batch_and_hint(mods):
     for it in range(4):
         outs.append(ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, **kw))
         torch.cuda.synchronize()
-    e, all_rect = ldi._POSE_CACHE.lookup((k_s, k_t, rot, t))
-    assert all_rect and e['state'] is True
+    e, cls = ldi._POSE_CACHE.lookup((k_s, k_t, rot, t))
+    assert cls == 'all' and e['state'] == 'all'
     ref = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, _variant=1, **kw)
     for o in outs:
         for a, b in zip(o, ref):
             assert rel_err(a.cpu(), b.cpu()) < 2e-5
     # an in-place change of the cameras (now outside the class) must drop the hint
     rot.copy_(_scene(L, B, H, W, seed=6, rotate=(0,))[5].cuda())
-    e, all_rect = ldi._POSE_CACHE.lookup((k_s, k_t, rot, t))
-    assert not all_rect
+    e, cls = ldi._POSE_CACHE.lookup((k_s, k_t, rot, t))
+    assert cls is None
     got = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, **kw)
     ref = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, _variant=1, **kw)
     for a, b in zip(got, ref):
         assert torch.isfinite(a).all()
         assert rel_err(a.cpu(), b.cpu()) < 2e-5
+
+
+def test_no_image_in_class_hint(mods):
+    """General poses for the whole batch: after the first sight the mirror passes variant 6 (no row-gather launch); same result."""
+    ldi, helpers = mods
+    L, B, H, W = 2, 3, 16, 64
+    kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=1e-3, max_disp=0.4, zbuf_scale=50)
+    tex, mask, disp, k_s, k_t, rot, t = [x.cuda() for x in _scene(L, B, H, W, seed=11, rotate=(0, 1, 2))]
+    pc = helpers.pixel_coords(B, H, W)
+    outs = []
+    for it in range(3):
+        outs.append(ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, **kw))
+        torch.cuda.synchronize()
+    assert ldi._POSE_CACHE.lookup((k_s, k_t, rot, t))[1] == 'none'
+    ref = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, _variant=1, **kw)
+    for o in outs:
+        for a, b in zip(o, ref):
+            assert rel_err(a.cpu(), b.cpu()) < 2e-5
 
 
 def test_rowgather_gradients_unchanged(mods):
