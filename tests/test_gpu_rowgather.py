@@ -132,6 +132,27 @@ def test_rowgather_mixed_batch_and_hint(mods):
         assert rel_err(a.cpu(), b.cpu()) < 2e-5
 
 
+def test_rowgather_empty_rows_and_loud_misuse(mods):
+    """A vertical offset leaves target rows that no source row reaches (background only: the producer's data-less items); and the
+    all-rectified hint forced onto a batch that is NOT in the class must fail loudly (NaNs), never silently."""
+    ldi, helpers = mods
+    L, B, H, W = 2, 2, 32, 96
+    kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=1e-3, max_disp=0.4, zbuf_scale=50)
+    # pure vertical offset through the principal point (still rectified: y' = y + const): rows shifted out of the image
+    tex, mask, disp, k_s, k_t, rot, t = [x.cuda() for x in _scene(L, B, H, W, seed=22)]
+    k_t = k_t.clone(); k_t[:, 1, 2] += 9.5
+    pc = helpers.pixel_coords(B, H, W)
+    got = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, **kw)
+    ref = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, _variant=1, **kw)
+    for a, b in zip(got, ref):
+        assert rel_err(a.cpu(), b.cpu()) < 2e-5
+    assert torch.allclose(got[0][0, :, :8], torch.ones_like(got[0][0, :, :8]))      # the first rows see only the white canvas
+    # misuse: variant 5 on rotated cameras
+    sc = _scene(L, B, H, W, seed=23, rotate=(1,))
+    img, wts = _run(ldi, helpers, sc, True, True, 5, **kw)
+    assert torch.isfinite(img[0, 0]).all() and torch.isnan(img[0, 1]).all() and torch.isnan(wts[0, 1]).all()
+
+
 def test_no_image_in_class_hint(mods):
     """General poses for the whole batch: after the first sight the mirror passes variant 6 (no row-gather launch); same result."""
     ldi, helpers = mods
