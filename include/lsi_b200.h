@@ -50,6 +50,15 @@ LSI_B200_API unsigned long long lsi_b200_launch_count(void);
 LSI_B200_API int lsi_b200_kernel_timing_enable(int on);
 LSI_B200_API int lsi_b200_kernel_timing_collect(double* ms_by_kind, int* launches_by_kind);
 
+/* Prepared-weights memo of the tensor-core convolutions (lsi_b200_conv2d_tc*, lsi_b200_conv2d_halo*): the K-major / fp16 / split
+ * re-layout of a filter bank depends on the weights only.  A caller that knows a weight tensor has not changed since it last passed
+ * `version` for it sets that (non-zero) version immediately before the conv call; the call consumes it, keeps the re-laid-out filter in
+ * library-owned device memory per (weight pointer, layout) and rebuilds it only when the version differs.  Without a version (the
+ * default, and every training-path call) the filter is re-laid-out into the caller's workspace as before.  The reference has no
+ * counterpart: slim.conv2d reads its variable directly (nets.py:263-348). */
+LSI_B200_API void lsi_b200_set_weight_version(unsigned long long version);
+LSI_B200_API void lsi_b200_weight_cache_clear(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Renderer: lsi/geometry/ldi.py:71-182 forward_splat (+ projection.py:71-86, helpers.py:82-85,116-137,
  * 180-193, sampling.py:171-313 fused inside).

@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: version, thread-local error text, launch counter.
 #include <atomic>
+#include <mutex>
 #include <string.h>
 #include <vector>
 
@@ -36,7 +37,52 @@ ScopedTiming::~ScopedTiming() {
   if (on) { cudaEventRecord(b, st); g_timed.push_back(TimedLaunch{a, b, kind}); }
 }
 
+// ---- prepared-weights memo (tensor-core conv kernels): the K-major / fp16 / split re-layout of a filter is a function of the weights
+// only, yet it ran as a launch in front of every convolution (~50 launches, 2 % of the inference step).  A caller that can vouch for
+// "these weights have not changed" passes a non-zero version for the NEXT conv call (lsi_b200_set_weight_version); the re-laid-out
+// filter is then kept in library-owned device memory per (weight pointer, layout signature) and rebuilt only when the version moves.
+struct PrepEntry { const void* w; unsigned long long ver; int sig[12]; void* buf; size_t bytes; };
+static std::vector<PrepEntry> g_prep;
+static std::mutex g_prep_mu;
+static thread_local unsigned long long g_next_weight_version = 0;
+
+unsigned long long take_weight_version() {
+  const unsigned long long v = g_next_weight_version;
+  g_next_weight_version = 0;
+  return v;
+}
+
+void* prep_cache_get(const void* w, unsigned long long ver, const int* sig, size_t bytes, bool* hit) {
+  std::lock_guard<std::mutex> lock(g_prep_mu);
+  *hit = false;
+  for (PrepEntry& e : g_prep) {
+    if (e.w == w && e.bytes == bytes && memcmp(e.sig, sig, sizeof(e.sig)) == 0) {
+      *hit = e.ver == ver;
+      e.ver = ver;
+      return e.buf;
+    }
+  }
+  if (g_prep.size() >= 1024) {      // pointers recycled by many short-lived weight tensors: start over
+    for (PrepEntry& e : g_prep) cudaFree(e.buf);
+    g_prep.clear();
+  }
+  PrepEntry e;
+  e.w = w; e.ver = ver; e.bytes = bytes; e.buf = nullptr;
+  memcpy(e.sig, sig, sizeof(e.sig));
+  if (cudaMalloc(&e.buf, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }   // no memory: the caller re-lays-out into its workspace
+  g_prep.push_back(e);
+  return e.buf;
+}
+
 }  // namespace lsi
+
+extern "C" void lsi_b200_set_weight_version(unsigned long long version) { lsi::g_next_weight_version = version; }
+
+extern "C" void lsi_b200_weight_cache_clear(void) {
+  std::lock_guard<std::mutex> lock(lsi::g_prep_mu);
+  for (lsi::PrepEntry& e : lsi::g_prep) cudaFree(e.buf);
+  lsi::g_prep.clear();
+}
 
 extern "C" int lsi_b200_version(void) { return 100; }
 extern "C" const char* lsi_b200_last_error(void) { return lsi::g_err; }

@@ -10,6 +10,10 @@ namespace lsi {
 
 void set_error(const char* fmt, ...);
 void count_launch(unsigned n = 1);
+// prepared-weights memo (capi.cu): the version the caller set for this conv call (0 = none), and the device buffer that holds / will hold
+// the re-laid-out filter for (w, sig); *hit = its content is current
+unsigned long long take_weight_version();
+void* prep_cache_get(const void* w, unsigned long long ver, const int* sig, size_t bytes, bool* hit);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -930,6 +930,7 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
                            const float* in_bn_stats, const float* in_bn_beta,
                            const float* w, const float* bias, const float* out_scale, void* out, int out_f16, float* out_bn_stats,
                            float bn_eps, void* workspace, size_t workspace_bytes, void* stream, int split = 0) {
+  const unsigned long long wver = take_weight_version();   // consumed by this call whatever happens next
   LSI_REQUIRE(d && in && w && out && workspace, "NULL pointer argument");
   HaloPlan pl;
   LSI_REQUIRE(split ? halo_plan(d, &pl, false, false, false, true) : (halo_plan(d, &pl) || (in_f16 && halo_plan(d, &pl, true, true))),
@@ -982,10 +983,18 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   p.halo_w = pl.halo_w; p.halo_h = pl.halo_h; p.halo_bytes = pl.halo_bytes; p.b_tap_bytes = pl.b_tap_bytes; p.w_bytes = pl.w_bytes;
   p.div_halo_w = 65536u / (uint32_t)pl.halo_w + 1u;
 
-  // weights -> K-major [tap][n_tile][cin]
-  float* wk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  // weights -> K-major [tap][n_tile][cin]: into the workspace, or -- when the caller vouched for a weight version -- into the memo
+  float* const wk_ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* wk = wk_ws;
   const int taps = d->kh * d->kw;
-  {
+  bool prep_needed = true;
+  if (wver) {
+    const int sig[12] = {2, split ? 2 : (f16 ? 1 : 0), taps, d->c_in, d->c_out, pl.n_tile, d->mode, d->w_tap_stride, d->w_ci_stride, d->w_co_stride, 0, 0};
+    bool hit = false;
+    void* buf = prep_cache_get(w, wver, sig, (size_t)taps * pl.n_tile * d->c_in * sizeof(float) * (split ? 2 : 1), &hit);
+    if (buf) { wk = static_cast<float*>(buf); prep_needed = !hit; }
+  }
+  if (prep_needed) {
     const long long total = (long long)taps * pl.n_tile * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
     if (split)
@@ -1044,7 +1053,7 @@ static int conv2d_halo_impl(const lsi_b200_conv_desc* d, const void* in, const v
   n_ctas = n_ctas / G * G;
   if (n_ctas < G) n_ctas = G;
   if (out_bn_stats) {
-    p.stat_part = wk + (size_t)taps * pl.n_tile * d->c_in * (split ? 2 : 1);
+    p.stat_part = wk_ws + (size_t)taps * pl.n_tile * d->c_in * (split ? 2 : 1);
     p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
   }
   {

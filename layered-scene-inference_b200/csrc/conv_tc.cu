@@ -684,6 +684,7 @@ extern "C" int lsi_b200_conv2d_tc_bnstats(const lsi_b200_conv_desc* d, const flo
 static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_in_a, const void* in_b, int in_b_c_stride,
                           const float* w, const float* bias, void* out, float* bn_stats, float bn_eps, void* workspace,
                           size_t workspace_bytes, void* stream, int h16, int out_f16, const float* out_scale) {
+  const unsigned long long wver = take_weight_version();   // consumed by this call whatever happens next
   LSI_REQUIRE(d && in_a && w && out && workspace, "NULL pointer argument");
   if (h16 == 2 && split_variant_l()) h16 = 3;
   LSI_REQUIRE(h16 != 1 || (d->in_c_stride % 8 == 0 && (!in_b || in_b_c_stride % 8 == 0)), "fp16 activations need 8-channel-aligned pixel strides");
@@ -735,10 +736,18 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad_t = d->pad_top; p.pad_l = d->pad_left; p.mode = d->mode;
   p.epilogue = d->epilogue; p.accumulate = d->accumulate;
 
-  // weights -> K-major [tap][n_pad][cin]
-  float* wk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  // weights -> K-major [tap][n_pad][cin]: into the workspace, or -- when the caller vouched for a weight version -- into the memo
+  float* const wk_ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* wk = wk_ws;
   const int taps = d->kh * d->kw;
-  {
+  bool prep_needed = true;
+  if (wver) {
+    const int sig[12] = {1, h16, taps, d->c_in, d->c_out, p.n_pad, p.n_tile, d->w_tap_stride, d->w_ci_stride, d->w_co_stride, 0, 0};
+    bool hit = false;
+    void* buf = prep_cache_get(w, wver, sig, (size_t)taps * p.n_pad * d->c_in * sizeof(float) * ((h16 == 2) ? 2 : 1), &hit);
+    if (buf) { wk = static_cast<float*>(buf); prep_needed = !hit; }
+  }
+  if (prep_needed) {
     const long long total = (long long)taps * p.n_pad * d->c_in;
     long long g = (total + 255) / 256; if (g > 148 * 8) g = 148 * 8;
     if (h16 == 3)
@@ -816,7 +825,7 @@ static int conv2d_tc_impl(const lsi_b200_conv_desc* d, const void* in_a, int c_i
   dim3 grid((unsigned)n_ctas);
   p.stat_part = nullptr;
   if (bn_stats) {
-    p.stat_part = wk + (size_t)taps * p.n_pad * d->c_in * ((h16 == 2) ? 2 : 1);   // (variant L: the fp16 pair rows take the fp32 size)
+    p.stat_part = wk_ws + (size_t)taps * p.n_pad * d->c_in * ((h16 == 2) ? 2 : 1);   // (variant L: the fp16 pair rows take the fp32 size)
     p.stat_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.stat_part) + 255) & ~uintptr_t(255));
     LSI_CUDA(cudaMemsetAsync(p.stat_part, 0, (size_t)n_ctas * 4 * p.n_pad * 2 * sizeof(float), st));
   }

@@ -38,6 +38,8 @@ SIGNATURES = {
     'lsi_b200_last_error': (ctypes.c_char_p, []),
     'lsi_b200_launch_count': (ctypes.c_ulonglong, []),
     'lsi_b200_kernel_timing_enable': (_I, [_I]),
+    'lsi_b200_set_weight_version': (None, [ctypes.c_ulonglong]),
+    'lsi_b200_weight_cache_clear': (None, []),
     'lsi_b200_kernel_timing_collect': (_I, [_P, _P]),
     'lsi_b200_projection_matrix': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     'lsi_b200_forward_splat_workspace_bytes': (_SZ, [_DP]),

@@ -40,12 +40,25 @@ class ParamStore(object):
     """TF-variable-scope stand-in: name -> leaf tensor.  `flatten()` re-packs every variable (and its gradient) into
     one contiguous buffer each, which is what the NCCL all-reduce and the fused Adam kernel operate on."""
 
+    _epochs = [0]        # process-wide: no two stores, and no two parameter states of one store, ever share an epoch
+
     def __init__(self, device='cuda', seed=0):
         self.device = torch.device(device)
         self.seed = seed
         self.vars = {}
         self.flat = None
         self.flat_grad = None
+        self.touch()
+
+    def touch(self):
+        """Call after changing parameter VALUES by anything that does not move the tensors' version counters (a kernel writing through
+        raw pointers: the fused Adam step).  The inference path memoises re-laid-out filters per (weight tensor, epoch, version)."""
+        ParamStore._epochs[0] += 1
+        self.epoch = ParamStore._epochs[0]
+
+    def weight_version(self, w):
+        """Non-zero 64-bit tag that changes whenever `w` may hold different values: this store's epoch and the tensor's version."""
+        return ((self.epoch & 0xffffffff) << 32) | ((w._version + 1) & 0xffffffff)
 
     def get(self, name, shape, reuse, kind):
         if name in self.vars:
@@ -79,6 +92,7 @@ class ParamStore(object):
                 if self.flat is not None:
                     raise RuntimeError('ParamStore is already flattened')
                 self.vars[k] = t.clone().requires_grad_(True)
+        self.touch()
 
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self.vars.items()}
@@ -101,6 +115,7 @@ class ParamStore(object):
             self.vars[k] = nv
             off += m
         self.flat, self.flat_grad = flat, grad
+        self.touch()
         return flat, grad
 
     def zero_grad(self):
@@ -238,6 +253,17 @@ def _tc_workspace(device, nbytes):
     return _tc_ws[key]
 
 
+_WEIGHT_MEMO = os.environ.get('LSI_B200_WEIGHT_MEMO', '1') != '0'
+
+
+def _vouch(store, w):
+    """Inference path (no_grad): tell the library that `w` is unchanged since the last call that passed the same tag, so that the
+    K-major / fp16 / split re-layout of the filter (a launch in front of every tensor-core convolution) is reused instead of redone
+    (lsi_b200_set_weight_version, include/lsi_b200.h).  Must be followed immediately by the conv call, which consumes the tag."""
+    if _WEIGHT_MEMO and store is not None and not torch.is_grad_enabled():
+        _b200.lib().lsi_b200_set_weight_version(store.weight_version(w))
+
+
 def _tc_ok(d, c_in_a, *tensors):
     return (_tc_mode() and _b200.lib().lsi_b200_conv2d_tc_supported(d, c_in_a) == 1
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
@@ -351,7 +377,7 @@ def _halo_ok(d, *tensors):
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
 
 
-def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None, x_b=None):
+def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None, x_b=None, store=None):
     """One halo-tile launch; x: tensor or _Pending (normalised on load); x_b: optional second source (already normalised),
     i.e. tf.concat([x, x_b], axis=3) on the fly."""
     lib = _b200.lib()
@@ -359,6 +385,7 @@ def _conv_halo(d, x, w, out, bias=None, out_stats=None, out_scale=None, x_b=None
     xin = x.z if pend else x
     nws = int(lib.lsi_b200_conv2d_halo_workspace_bytes(d))
     ws = _tc_workspace(xin.device, nws)
+    _vouch(store, w)          # (inference call sites pass their store; the training path does not)
     _b200.call('lsi_b200_conv2d_halo_h', d, _b200.ptr(xin), _b200.ptr(x_b), xin.shape[3], 0 if x_b is None else x_b.shape[3],
                int(xin.dtype == torch.float16),
                _b200.ptr(x.stats) if pend else None, _b200.ptr(x.beta) if pend else None, _b200.ptr(w), _b200.ptr(bias),
@@ -579,6 +606,7 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
             z = _SplitAct.empty(B, geo.Ho, geo.Wo, cout, a.device)
             stats = torch.empty(cout, 2, dtype=torch.float32, device=a.device)
             ws = _tc_workspace(a.device, int(lib.lsi_b200_conv2d_halo_workspace_bytes(d)))
+            _vouch(store, w)
             _b200.call('lsi_b200_conv2d_halo_s', d, _b200.ptr(a.t), _b200.ptr(x.stats) if pend else None,
                        _b200.ptr(x.beta) if pend else None, _b200.ptr(w), None, None, _b200.ptr(z.t), 2, _b200.ptr(stats), BN_EPS,
                        _b200.ptr(ws), ws.numel(), _b200.stream())
@@ -623,6 +651,7 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
     z = _SplitAct.empty(B, geo.Ho, geo.Wo, cout, a.device)
     stats = torch.empty(cout, 2, dtype=torch.float32, device=a.device)
     ws = _tc_workspace(a.device, int(lib.lsi_b200_conv2d_tc_workspace_bytes(d)))
+    _vouch(store, w)
     _b200.call('lsi_b200_conv2d_tc_s', d, _b200.ptr(a.t), ca, None if b is None else _b200.ptr(b.t), 0 if b is None else b.shape[3],
                _b200.ptr(w), None, None, _b200.ptr(z.t), 2, _b200.ptr(stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
     out = _Pending(z, stats, beta)
@@ -657,7 +686,7 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
             beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
             z = torch.empty(geo.B, geo.Ho, geo.Wo, cout, dtype=torch.float16, device=pb.device)
             stats = torch.empty(cout, 2, dtype=torch.float32, device=pb.device)
-            _conv_halo(d, pa, w, z, out_stats=stats, x_b=pb)
+            _conv_halo(d, pa, w, z, out_stats=stats, x_b=pb, store=store)
             out = _Pending(z, stats, beta)
             return out if defer else out.materialize()
         if pair:
@@ -680,7 +709,7 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
             z_dt = torch.float16 if (h or (defer and _HALO_F16_STORE and cout == 32)) else torch.float32
             z = torch.empty(B, geo.Ho, geo.Wo, cout, dtype=z_dt, device=dev)
             stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
-            _conv_halo(d, a, w, z, out_stats=stats)
+            _conv_halo(d, a, w, z, out_stats=stats, store=store)
             done = True
         else:
             a = _materialize(a)
@@ -690,6 +719,7 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
                 stats = torch.empty(cout, 2, dtype=torch.float32, device=dev)
                 nws = int(_b200.lib().lsi_b200_conv2d_tc_workspace_bytes(d))
                 ws = _tc_workspace(dev, nws)
+                _vouch(store, w)
                 _b200.call('lsi_b200_conv2d_tc_h', d, _b200.ptr(a), ca, _b200.ptr(b), 0 if b is None else b.shape[-1], _b200.ptr(w),
                            None, _b200.ptr(z), 1, _b200.ptr(stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
                 done = True
@@ -779,12 +809,14 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
             if _HALO and nc <= 4 and lib.lsi_b200_conv2d_halo_s_supported(dp) == 1:
                 fa = feat_l.z if isinstance(feat_l, _Pending) else feat_l
                 ws = _tc_workspace(fa.device, int(lib.lsi_b200_conv2d_halo_workspace_bytes(dp)))
+                _vouch(store, w)
                 _b200.call('lsi_b200_conv2d_halo_s', dp, _b200.ptr(fa.t), _b200.ptr(feat_l.stats) if pend else None,
                            _b200.ptr(feat_l.beta) if pend else None, _b200.ptr(w), _b200.ptr(b), _b200.ptr(_out_scale), _b200.ptr(y), 0,
                            None, BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
             else:
                 fm = _materialize(feat_l)
                 ws = _tc_workspace(fm.device, int(lib.lsi_b200_conv2d_tc_workspace_bytes(dp)))
+                _vouch(store, w)
                 _b200.call('lsi_b200_conv2d_tc_s', dp, _b200.ptr(fm.t), cin, None, 0, _b200.ptr(w), _b200.ptr(b), _b200.ptr(_out_scale),
                            _b200.ptr(y), 0, None, BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
             preds.append(y)
@@ -792,7 +824,7 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
             if packed is None and l == 0:
                 packed = torch.empty(n_layers, B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
             y = packed[l] if packed is not None else torch.empty(B, geo.Ho, geo.Wo, nc, dtype=torch.float32, device=feat_l.device)
-            _conv_halo(dp, feat_l, w, y, bias=b, out_scale=_out_scale)
+            _conv_halo(dp, feat_l, w, y, bias=b, out_scale=_out_scale, store=store)
             preds.append(y)
         else:
             fm = _materialize(feat_l)

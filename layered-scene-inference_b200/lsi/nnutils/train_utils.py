@@ -442,5 +442,6 @@ class Trainer(object):
         _b200.call('lsi_b200_adam_step', _b200.ptr(self.store.flat), _b200.ptr(self.store.flat_grad), _b200.ptr(self.m),
                    _b200.ptr(self.v), self.store.flat.numel(), o.learning_rate, o.beta1, 0.999, 1e-8, self.adam_t,
                    1.0 / world, _b200.stream())
+        self.store.touch()        # parameter values changed through raw pointers: invalidate the inference path's filter memo
         out = (total.detach(), {k: (v.detach() if torch.is_tensor(v) else v) for k, v in parts.items()})
         return out + (chk,) if dp_check else out

@@ -231,3 +231,38 @@ def test_split_mode_with_autograd_runs_exact_kernels(nets_split):
     store = nets_split.ParamStore()
     out = nets_split._conv_layer(store, 't', x, 32, 3, 1, reuse=False)
     assert isinstance(out, torch.Tensor) and out.dtype == torch.float32 and out.requires_grad
+
+
+@pytest.mark.parametrize('cin,cout,H,W', [(64, 64, 16, 16), (32, 32, 16, 24)])      # generic kernel / halo-tile kernel
+def test_filter_memo_follows_the_weights(nets_split, cin, cout, H, W):
+    """The inference path memoises the re-laid-out (split) filter bank per (weight tensor, store epoch, tensor version)
+    (lsi_b200_set_weight_version).  It must never serve a stale filter: in-place updates (version counter), a new store whose weight
+    tensor lands on the same address, and raw-pointer updates followed by ParamStore.touch() (what Trainer.train_step does after the
+    fused Adam kernel) all have to show up in the next forward pass -- bit for bit what a fresh store gives."""
+    nets = nets_split
+    torch.manual_seed(5)
+    x = torch.randn(2, H, W, cin).cuda()
+    ws = [torch.randn(3, 3, cin, cout) / (9 * cin) ** 0.5 for _ in range(4)]
+    beta = torch.randn(cout) * 0.3
+
+    def fresh(w):
+        st = nets.ParamStore()
+        st.load_state_dict({'t/weights': w, 't/BatchNorm/beta': beta})
+        with torch.no_grad():
+            return nets._conv_layer(st, 't', x, cout, 3, 1, reuse=True).float()
+
+    want = [fresh(w) for w in ws]
+    assert not torch.equal(want[0], want[1])
+    store = nets.ParamStore()
+    store.load_state_dict({'t/weights': ws[0], 't/BatchNorm/beta': beta})
+    run = lambda: nets._conv_layer(store, 't', x, cout, 3, 1, reuse=True).float()
+    with torch.no_grad():
+        assert torch.equal(run(), want[0])
+        assert torch.equal(run(), want[0])                       # memo hit
+        store.vars['t/weights'].copy_(ws[1].cuda())              # in-place update: version counter
+        assert torch.equal(run(), want[1])
+        store.load_state_dict({'t/weights': ws[2]})              # epoch
+        assert torch.equal(run(), want[2])
+        store.vars['t/weights'].data.copy_(ws[3].cuda())         # a write the version counter does not see ...
+        store.touch()                                            # ... announced the way Trainer.train_step announces the Adam kernel
+        assert torch.equal(run(), want[3])
