@@ -12,14 +12,18 @@
 //     vertical weight, output offset) and streams the W pixels x 16 B into a shared-memory ring with 1-D bulk copies
 //     (cp.async.bulk, mbarrier completion; full / empty barriers per slot);
 //   * the consumer warps run two passes per item:
-//       pass 1 (thread = source pixel): projection, z-buffer weight, horizontal corner weights, thresholds; the weighted
-//         value (w*rgb, w) replaces the pixel in the stage, the two corner weights go to small arrays, and the pixel links
-//         itself into the list of its left target cell with ONE integer ATOMS.EXCH (measured 2 SM-cycles per warp
-//         instruction on B200, tools/micro/atoms_bench.cu -- the float atomics a shared-memory scatter would need are CAS
-//         loops).  List heads carry a 16-bit generation tag, so they are never cleared between items;
-//       pass 2 (thread = target cell): walks the list of its own cell (left weights) and of its left neighbour's cell
-//         (right weights) and accumulates in REGISTERS -- a gather, no float atomics anywhere;
-//   * after the last item of a row the thread normalises (ldi.py:165-173, bg canvas folded in) and stores its cells once.
+//       pass 1 (thread = 4 source pixels): projection, z-buffer weight, horizontal corner weights, thresholds; the weighted
+//         value (w*rgb, w) replaces the pixel in the stage (packed rows) or goes to a node array (planar rows), the two corner
+//         weights go to an 8-byte slot, and the pixel links itself into the list of its left target cell with ONE integer
+//         ATOMS.EXCH (measured 2 SM-cycles per warp instruction on B200, tools/micro/atoms_bench.cu -- the float atomics a
+//         shared-memory scatter would need are CAS loops).  List heads carry a 16-bit generation tag, so they are never
+//         cleared between items;
+//       pass 2 (thread = 4 lists): list j holds the pixels whose left cell is j - 1 and whose right cell is j; one walk per
+//         list accumulates the left-weighted values for cell j - 1 and the right-weighted values for cell j in REGISTERS,
+//         across all items of the row -- a gather, no float atomics anywhere;
+//   * after the last item of a row neighbouring threads exchange the halves that belong to each other's cell (shuffle; warp
+//     boundaries through a few hundred bytes of shared memory), then the thread normalises (ldi.py:165-173, bg canvas folded
+//     in) and stores its cells once.
 //
 // HBM traffic = the algorithmic bytes (every source row read once when it maps to one target row, otherwise again through
 // L2; every target pixel written once); no accumulator, no memset, no normalise launch.  Same per-pixel formulas as
