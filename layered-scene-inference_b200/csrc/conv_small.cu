@@ -179,7 +179,7 @@ extern "C" int lsi_b200_conv2d_stem_wgrad(const lsi_b200_conv_desc* d, const flo
                     d->pad_left, d->in_c_stride, d->out_c_stride, 0, 0};
   p.tiles_x = (d->w_out + kSwTile - 1) / kSwTile;
   p.tiles = (long long)d->batch * d->h_out * p.tiles_x;
-  LSI_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->kh * d->kw * d->c_in * 32 * sizeof(float), st));
+  if (!d->accumulate) LSI_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->kh * d->kw * d->c_in * 32 * sizeof(float), st));
   const int patch_w = (kSwTile - 1) * d->stride + d->kw;
   const size_t smem = ((size_t)d->kh * patch_w * d->c_in + kSwTile * 32) * sizeof(float);
   long long grid = 148 * 4;

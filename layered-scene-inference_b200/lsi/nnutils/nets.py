@@ -269,7 +269,7 @@ def _tc_ok(d, c_in_a, *tensors):
             and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
 
 
-def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=None):
+def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=None, store=None):
     """One convolution launch.  inp_b: optional second source (channels [c_in_a, c_in)), i.e. tf.concat on the fly
     (tensor-core path only).  bn_stats: [C,2] tensor to receive (mean, rsqrt(var+eps)) of the output, reduced in the conv
     epilogue (tensor-core path only).  Returns True when bn_stats was filled."""
@@ -280,12 +280,13 @@ def _conv(desc_kw, inp, w, out, bias=None, bn_stats=None, inp_b=None, c_in_a=Non
             and inp.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and lib.lsi_b200_conv2d_halo_supported(d) == 1):
         # full-resolution 32/64-channel head layers, also inside the training step (forward convs, the data gradient of
         # upcnv1b): resident filter bank + one halo box per tile instead of one box per tap
-        _conv_halo(d, inp, w, out, bias=bias, out_stats=bn_stats)
+        _conv_halo(d, inp, w, out, bias=bias, out_stats=bn_stats, store=store)
         return bn_stats is not None
     if _tc_ok(d, ca, inp, inp_b):
         nws = int(lib.lsi_b200_conv2d_tc_workspace_bytes(d))
         ws = _tc_workspace(inp.device, nws)
         cb_stride = 0 if inp_b is None else inp_b.shape[-1]
+        _vouch(store, w)      # (the two towers of a training step share their filters: the second one reuses the re-laid-out banks)
         if bn_stats is not None and d.epilogue == 0 and d.accumulate == 0:
             _b200.call('lsi_b200_conv2d_tc_bnstats', d, _b200.ptr(inp), ca, _b200.ptr(inp_b), cb_stride, _b200.ptr(w),
                        _b200.ptr(out), _b200.ptr(bn_stats), BN_EPS, _b200.ptr(ws), ws.numel(), _b200.stream())
@@ -451,6 +452,38 @@ def _sync_bn_world():
     return _SYNC_BN[0], dist.get_world_size(_SYNC_BN[0])
 
 
+_GRAD_SINK = [False]
+
+
+class grad_sink(object):
+    """Inside this context the backward passes of the conv layers add their weight gradients straight into `weights.grad` (the
+    weight-gradient kernels take an accumulate flag) and hand autograd `None` for them -- no temporary, no memset, no separate
+    accumulation launch per use of a variable (a training step uses every filter twice: two towers).  Only for leaves whose
+    `.grad` already exists as a dense tensor, i.e. after `ParamStore.flatten()` + `zero_grad()`: what Trainer.train_step does."""
+
+    def __enter__(self):
+        self.prev = _GRAD_SINK[0]
+        _GRAD_SINK[0] = True
+
+    def __exit__(self, *exc):
+        _GRAD_SINK[0] = self.prev
+        return False
+
+
+def _sink_of(w):
+    return w if (_GRAD_SINK[0] and w.is_leaf and w.grad is not None and w.grad.is_contiguous() and w.grad.dtype == torch.float32) else None
+
+
+def _wgrad_into(ctx_leaf, geo, big, small, like):
+    """Weight gradient of one use of a filter: into the leaf's .grad (accumulating) when a sink is active, else a fresh tensor."""
+    if ctx_leaf is not None and ctx_leaf.grad is not None:
+        _wgrad(dict(geo.wgrad, accumulate=1), big, small, ctx_leaf.grad)
+        return None
+    dw = torch.empty_like(like)
+    _wgrad(geo.wgrad, big, small, dw)
+    return dw
+
+
 class _ConvBNReLU(torch.autograd.Function):
     """slim.conv2d / slim.conv2d_transpose with normalizer_fn=batch_norm and activation relu (nets.py:263-272)."""
 
@@ -459,7 +492,7 @@ class _ConvBNReLU(torch.autograd.Function):
         dev = x.device
         z = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout, dtype=torch.float32, device=dev)
         stats = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
-        have_stats = _conv(geo.fwd, x, w, z, bn_stats=stats)        # tensor-core path reduces the BN statistics in its epilogue
+        have_stats = _conv(geo.fwd, x, w, z, bn_stats=stats, store=getattr(geo, 'store', None))        # tensor-core path reduces the BN statistics in its epilogue
         y = torch.empty_like(z)
         P = geo.B * geo.Ho * geo.Wo
         group, world = _sync_bn_world()
@@ -479,6 +512,7 @@ class _ConvBNReLU(torch.autograd.Function):
                    _b200.stream())
         ctx.save_for_backward(x, w, z, y, stats, beta)
         ctx.geo = geo
+        ctx.w_leaf = _sink_of(w)
         return y
 
     @staticmethod
@@ -503,21 +537,17 @@ class _ConvBNReLU(torch.autograd.Function):
             # dense fast path: reads z and dy only (ReLU mask recomputed from z exactly as the forward kernel evaluates it)
             _b200.call('lsi_b200_bn_relu_backward_z', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
                        _b200.ptr(sums), P, geo.Cout, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
-            dbeta = sums[:, 0].contiguous()
+            dbeta = sums[:, 0]        # (a strided view: autograd accumulates it as it is -- no copy launch)
         else:
             _b200.call('lsi_b200_bn_relu_backward', _b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
                        _b200.ptr(sums), P, geo.Cout, geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0,
                        _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
-            dbeta = sums[:, 0].contiguous()
+            dbeta = sums[:, 0]        # (a strided view: autograd accumulates it as it is -- no copy launch)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _conv(geo.dgrad, dz, w, dx)
-        dw = torch.empty_like(w)
-        if geo.transposed:
-            _wgrad(geo.wgrad, dz, x, dw)
-        else:
-            _wgrad(geo.wgrad, x, dz, dw)
+            _conv(geo.dgrad, dz, w, dx, store=getattr(geo, 'store', None))
+        dw = _wgrad_into(ctx.w_leaf, geo, dz, x, w) if geo.transposed else _wgrad_into(ctx.w_leaf, geo, x, dz, w)
         return dx, dw, dbeta, None
 
 
@@ -527,9 +557,10 @@ class _ConvBiasSigmoid(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, geo):
         y = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout, dtype=torch.float32, device=x.device)
-        _conv(dict(geo.fwd, epilogue=2), x, w, y, bias)
+        _conv(dict(geo.fwd, epilogue=2), x, w, y, bias, store=getattr(geo, 'store', None))
         ctx.save_for_backward(x, w, y)
         ctx.geo = geo
+        ctx.w_leaf = _sink_of(w)
         return y
 
     @staticmethod
@@ -544,10 +575,9 @@ class _ConvBiasSigmoid(torch.autograd.Function):
         _b200.call('lsi_b200_channel_sums', _b200.ptr(dz), _b200.ptr(sums), geo.B * geo.Ho * geo.Wo, geo.Cout, geo.Cout,
                    _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
         dx = torch.empty_like(x)
-        _conv(geo.dgrad, dz, w, dx)
-        dw = torch.empty_like(w)
-        _wgrad(geo.wgrad, x, dz, dw)
-        return dx, dw, sums[:, 0].contiguous(), None
+        _conv(geo.dgrad, dz, w, dx, store=getattr(geo, 'store', None))
+        dw = _wgrad_into(ctx.w_leaf, geo, x, dz, w)
+        return dx, dw, sums[:, 0], None
 
 
 class _ConcatChannels(torch.autograd.Function):
@@ -754,6 +784,7 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
     geo = _Geometry(transposed, B, H, W, cin, cout, k, stride)
     w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
     beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
+    geo.store = store
     y = _ConvBNReLU.apply(x, w, beta, geo)
     return y.half() if _f16_infer() else y       # (the 3-channel stem: fp32 CUDA-core conv, handed on as fp16)
 
@@ -828,6 +859,7 @@ def pixelwise_predictor(feat, nc=3, n_layers=1, n_layerwise_steps=0, skip_feat=N
             preds.append(y)
         else:
             fm = _materialize(feat_l)
+            geo.store = store
             y = _ConvBiasSigmoid.apply(fm.float() if fm.dtype != torch.float32 else fm, w, b, geo)
             preds.append(y if _out_scale is None else y * _out_scale)
     if packed is not None and len(preds) == n_layers and all(p_.data_ptr() == packed[i].data_ptr() for i, p_ in enumerate(preds)):

@@ -420,9 +420,10 @@ class Trainer(object):
         if self.store.flat is None:
             self._build_variables(batch)
         self.store.zero_grad()
-        ldi_src, ldi_trg = self.define_pred_graph(batch['imgs_src'], batch['imgs_trg'])
-        total, parts = self.define_loss_graph(ldi_src, ldi_trg, batch)
-        total.backward()
+        with nets.grad_sink():      # weight gradients go straight into the flat gradient buffer (no temporaries, no accumulation launches)
+            ldi_src, ldi_trg = self.define_pred_graph(batch['imgs_src'], batch['imgs_trg'])
+            total, parts = self.define_loss_graph(ldi_src, ldi_trg, batch)
+            total.backward()
         chk = None
         g = self.store.flat_grad
         if dp_check:
