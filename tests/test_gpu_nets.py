@@ -211,3 +211,30 @@ def test_simple_encoder_decoder_golden(mode):
             assert e_feat < max(1e-3, 3 * n_feat) and e_pred < max(1e-4, 3 * n_pred)
     finally:
         nets.set_conv_mode('tf32')
+
+
+@pytest.mark.parametrize('mode', ['fwd', 'dgrad'])
+@pytest.mark.parametrize('H,W', [(9, 13), (16, 64)])
+def test_thin_conv_quad_kernel(mode, H, W):
+    """lsi_b200_conv2d_thin on the shape the training step sends it (data gradient of the 3x3 prediction conv, nets.py:139-155:
+    4 -> 32 channels; four pixels x eight channels per thread) and the same shape as a forward gather, against the generic fp32
+    kernel lsi_b200_conv2d on the same descriptor; widths that are not multiples of four, image borders, accumulate."""
+    from lsi import _b200
+    from lsi.nnutils import nets
+    torch.manual_seed(H + W)
+    B = 2
+    if mode == 'fwd':
+        geo = nets._Geometry(False, B, H, W, 4, 32, 3, 1)
+        desc, w = geo.fwd, torch.randn(3, 3, 4, 32, device='cuda')
+    else:
+        geo = nets._Geometry(False, B, H, W, 32, 4, 3, 1)
+        desc, w = geo.dgrad, torch.randn(3, 3, 32, 4, device='cuda')
+    x = torch.randn(B, H, W, 4, device='cuda')
+    for acc in (0, 1):
+        d = _b200.ConvDesc(**dict(desc, accumulate=acc))
+        assert _b200.lib().lsi_b200_conv2d_thin_supported(d) == 1
+        base = torch.randn(B, H, W, 32, device='cuda')
+        got, ref = base.clone(), base.clone()
+        _b200.call('lsi_b200_conv2d_thin', d, _b200.ptr(x), _b200.ptr(w), _b200.ptr(got), _b200.stream())
+        _b200.call('lsi_b200_conv2d', d, _b200.ptr(x), _b200.ptr(w), None, _b200.ptr(ref), _b200.stream())
+        assert rel_err(got.cpu(), ref.cpu()) < 1e-6
