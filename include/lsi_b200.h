@@ -344,6 +344,11 @@ LSI_B200_API int lsi_b200_bn_relu_backward(const float* x, const float* y, const
  * the raw conv output z and dy only (the mask is recomputed from z with the forward kernels' exact expression). */
 LSI_B200_API int lsi_b200_bn_relu_backward_z(const float* z, const float* beta, const float* dy, const float* stats, float* dx,
                                              float* dbeta_sums, long long n_pixels, int channels, void* workspace, void* stream);
+/* The same with dy read through a pixel stride (dy_c_stride >= channels, a multiple of 4): dy is the first `channels` channels of the
+ * gradient of tf.concat([this layer's output, skip], axis=3) (nets.py:108-109, 300), consumed where it lies. */
+LSI_B200_API int lsi_b200_bn_relu_backward_zs(const float* z, const float* beta, const float* dy, int dy_c_stride, const float* stats,
+                                              float* dx, float* dbeta_sums, long long n_pixels, int channels, void* workspace,
+                                              void* stream);
 /* lsi_b200_bn_relu_backward in two stages, for batch statistics that span several data-parallel ranks (the reference
  * normalises over the whole batch on one device, nets.py:263-272): stage 1 writes this rank's (sum dz, sum dz*xhat) to
  * dbeta_sums; the caller all-reduces them; stage 2 computes dx from the given sums with 1 / n_pixels_stat (global count). */

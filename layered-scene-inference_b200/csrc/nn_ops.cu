@@ -106,14 +106,18 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
   }
 }
 
-// dense fast path (x_cs == y_cs == C, C % 4 == 0, 16-byte aligned): 128-bit loads/stores, 32-bit channel arithmetic
+// fast path (x dense: x_cs == C; y dense or a channel slice of a wider tensor: y_cs % 4 == 0; C % 4 == 0, 16-byte aligned):
+// 128-bit loads/stores, 32-bit channel arithmetic
 __global__ void __launch_bounds__(256) bn_apply_vec4_kernel(const BnApplyParams p) {
   const long long total4 = p.P * p.C / 4;
   const unsigned c4n = (unsigned)p.C / 4;
   const float4* x = reinterpret_cast<const float4*>(p.x);
   float4* y = reinterpret_cast<float4*>(p.y);
+  const unsigned y_s4 = (unsigned)p.y_cs / 4;      // == c4n when y is dense; larger when y is a channel slice of a wider tensor
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((unsigned long long)i % c4n) * 4;
+    const unsigned long long q = (unsigned long long)i / c4n;
+    const unsigned c4 = (unsigned)((unsigned long long)i - q * c4n);
+    const int c = (int)c4 * 4;
     const float4 v = __ldcs(x + i);
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.stats + 2 * c)), s1 = __ldg(reinterpret_cast<const float4*>(p.stats + 2 * c) + 1);
     const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(256) bn_apply_vec4_kernel(const BnApplyParams 
     o.x = fmaf(v.x - s0.x, s0.y, b.x); o.y = fmaf(v.y - s0.z, s0.w, b.y);      // explicit fma: bn_bwd_z_* recompute the ReLU mask
     o.z = fmaf(v.z - s1.x, s1.y, b.z); o.w = fmaf(v.w - s1.z, s1.w, b.w);      // from z with exactly this expression
     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    y[i] = o;
+    y[q * y_s4 + c4] = o;
   }
 }
 
@@ -180,6 +184,7 @@ struct BnBwdZParams {
   const float4* z; const float4* dy; float4* dx;
   const float* beta; const float* stats; const float* sums; double* partial;
   long long total4, P; unsigned c4n; int C;
+  unsigned dy_s4;   // pixel stride of dy in float4 units (c4n when dy is dense; larger when dy is a channel slice of a concat gradient)
 };
 
 __global__ void __launch_bounds__(256) bn_bwd_z_stats_kernel(const BnBwdZParams p) {
@@ -190,8 +195,11 @@ __global__ void __launch_bounds__(256) bn_bwd_z_stats_kernel(const BnBwdZParams 
 #pragma unroll
   for (int k = 0; k < 4; ++k) { mean[k] = __ldg(p.stats + 2 * (c + k)); rstd[k] = __ldg(p.stats + 2 * (c + k) + 1); beta[k] = __ldg(p.beta + c + k); }
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long i = i0; i < p.total4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 zv = __ldcs(p.z + i), g = __ldcs(p.dy + i);
+  // (the grid stride is a multiple of c4n: a thread keeps its channels, its pixel advances by a constant)
+  long long j = (i0 / p.c4n) * p.dy_s4 + (i0 % p.c4n);
+  const long long jstep = ((long long)gridDim.x * blockDim.x / p.c4n) * p.dy_s4;
+  for (long long i = i0; i < p.total4; i += (long long)gridDim.x * blockDim.x, j += jstep) {
+    const float4 zv = __ldcs(p.z + i), g = __ldcs(p.dy + j);
     const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -225,8 +233,10 @@ __global__ void __launch_bounds__(256) bn_bwd_z_apply_kernel(const BnBwdZParams 
     mean[k] = __ldg(p.stats + 2 * (c + k)); rstd[k] = __ldg(p.stats + 2 * (c + k) + 1); beta[k] = __ldg(p.beta + c + k);
     m0[k] = __ldg(p.sums + 2 * (c + k)) * invP; m1[k] = __ldg(p.sums + 2 * (c + k) + 1) * invP;
   }
-  for (long long i = i0; i < p.total4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 zv = __ldcs(p.z + i), g = __ldcs(p.dy + i);
+  long long j = (i0 / p.c4n) * p.dy_s4 + (i0 % p.c4n);
+  const long long jstep = ((long long)gridDim.x * blockDim.x / p.c4n) * p.dy_s4;
+  for (long long i = i0; i < p.total4; i += (long long)gridDim.x * blockDim.x, j += jstep) {
+    const float4 zv = __ldcs(p.z + i), g = __ldcs(p.dy + j);
     const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, gg[4] = {g.x, g.y, g.z, g.w};
     float o[4];
 #pragma unroll
@@ -450,7 +460,7 @@ extern "C" int lsi_b200_bn_relu_forward(const float* x, const float* beta, float
     LSI_LAUNCH_CHECK();
   }
   BnApplyParams ap{x, stats, beta, y, n_pixels, channels, x_c_stride, y_c_stride, relu};
-  if (x_c_stride == channels && y_c_stride == channels && channels % 4 == 0 && ((uintptr_t)x & 15) == 0 &&
+  if (x_c_stride == channels && y_c_stride % 4 == 0 && channels % 4 == 0 && ((uintptr_t)x & 15) == 0 &&
       ((uintptr_t)y & 15) == 0 && ((uintptr_t)beta & 15) == 0)
     bn_apply_vec4_kernel<<<ew_grid(n_pixels * channels / 4), 256, 0, st>>>(ap);
   else
@@ -523,14 +533,21 @@ extern "C" int lsi_b200_channel_sums(const float* x, float* sums, long long n_pi
 // Dense fast path of lsi_b200_bn_relu_backward (contiguous [P, C] tensors, C % 4 == 0, ReLU): reads z and dy only.
 extern "C" int lsi_b200_bn_relu_backward_z(const float* z, const float* beta, const float* dy, const float* stats, float* dx,
                                            float* dbeta_sums, long long n_pixels, int channels, void* workspace, void* stream) {
+  return lsi_b200_bn_relu_backward_zs(z, beta, dy, channels, stats, dx, dbeta_sums, n_pixels, channels, workspace, stream);
+}
+
+extern "C" int lsi_b200_bn_relu_backward_zs(const float* z, const float* beta, const float* dy, int dy_c_stride, const float* stats,
+                                            float* dx, float* dbeta_sums, long long n_pixels, int channels, void* workspace,
+                                            void* stream) {
   LSI_REQUIRE(z && beta && dy && stats && dx && dbeta_sums && workspace, "NULL pointer argument");
+  LSI_REQUIRE(dy_c_stride >= channels && dy_c_stride % 4 == 0, "dy_c_stride must be a multiple of 4, >= channels");
   LSI_REQUIRE(n_pixels >= 1 && channels >= 4 && channels % 4 == 0 && channels <= 1024, "channels must be a multiple of 4 (<= 1024)");
   LSI_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0, "tensors must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   BnBwdZParams p;
   p.z = reinterpret_cast<const float4*>(z); p.dy = reinterpret_cast<const float4*>(dy); p.dx = reinterpret_cast<float4*>(dx);
   p.beta = beta; p.stats = stats; p.sums = dbeta_sums; p.partial = static_cast<double*>(workspace);
-  p.total4 = n_pixels * channels / 4; p.P = n_pixels; p.c4n = (unsigned)channels / 4; p.C = channels;
+  p.total4 = n_pixels * channels / 4; p.P = n_pixels; p.c4n = (unsigned)channels / 4; p.C = channels; p.dy_s4 = (unsigned)dy_c_stride / 4;
   // grid: a multiple of m blocks so that gridDim.x * 256 is a multiple of c4n (threads keep their channels across iterations)
   unsigned m = p.c4n, g256 = 256;
   while (g256) { const unsigned t = m % g256; m = g256; g256 = t; }   // m = gcd(c4n, 256)

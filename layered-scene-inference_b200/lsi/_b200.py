@@ -68,6 +68,7 @@ SIGNATURES = {
     'lsi_b200_conv2d_stem_wgrad_supported': (_I, [_CP]),
     'lsi_b200_conv2d_stem_wgrad': (_I, [_CP, _P, _P, _P, _P]),
     'lsi_b200_bn_relu_backward_z': (_I, [_P, _P, _P, _P, _P, _P, _LL, _I, _P, _P]),
+    'lsi_b200_bn_relu_backward_zs': (_I, [_P, _P, _P, _I, _P, _P, _P, _LL, _I, _P, _P]),
     'lsi_b200_conv2d_wgrad_tc_supported': (_I, [_CP]),
     'lsi_b200_conv2d_wgrad_tc': (_I, [_CP, _P, _P, _P, _P]),
     'lsi_b200_conv2d_tc_supported': (_I, [_CP, _I]),

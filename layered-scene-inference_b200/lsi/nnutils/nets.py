@@ -551,6 +551,48 @@ class _ConvBNReLU(torch.autograd.Function):
         return dx, dw, dbeta, None
 
 
+class _ConvBNReLUCat(torch.autograd.Function):
+    """_ConvBNReLU followed by tf.concat([., skip], axis=3) (nets.py:108-109, 300): the normalise + ReLU pass writes straight into the
+    first channels of the concat buffer, the skip is copied behind them (one copy instead of two), and the backward reads dy as a
+    channel slice of the concat gradient where it lies and returns the skip's share as a view (no copies).  Per-replica batch
+    statistics only (the caller falls back to the unfused layers under synchronised batch norm)."""
+
+    @staticmethod
+    def forward(ctx, x, w, beta, skip, geo):
+        dev = x.device
+        z = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout, dtype=torch.float32, device=dev)
+        stats = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+        have_stats = _conv(geo.fwd, x, w, z, bn_stats=stats, store=getattr(geo, 'store', None))
+        cb = skip.shape[3]
+        cat = torch.empty(geo.B, geo.Ho, geo.Wo, geo.Cout + cb, dtype=torch.float32, device=dev)
+        P = geo.B * geo.Ho * geo.Wo
+        _b200.call('lsi_b200_bn_relu_forward', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(cat), _b200.ptr(stats), P, geo.Cout,
+                   geo.Cout, geo.Cout + cb, BN_EPS, 1, 1 if have_stats else 0, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        _b200.call('lsi_b200_copy_channels', _b200.ptr(skip), ctypes_offset(cat, geo.Cout), P, cb, cb, geo.Cout + cb, 0, _b200.stream())
+        ctx.save_for_backward(x, w, z, stats, beta)
+        ctx.geo, ctx.cb = geo, cb
+        ctx.w_leaf = _sink_of(w)
+        return cat
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, z, stats, beta = ctx.saved_tensors
+        geo, cb = ctx.geo, ctx.cb
+        dev = x.device
+        g = g.contiguous()
+        P = geo.B * geo.Ho * geo.Wo
+        dz = torch.empty_like(z)
+        sums = torch.empty(geo.Cout, 2, dtype=torch.float32, device=dev)
+        _b200.call('lsi_b200_bn_relu_backward_zs', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(g), geo.Cout + cb, _b200.ptr(stats),
+                   _b200.ptr(dz), _b200.ptr(sums), P, geo.Cout, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _conv(geo.dgrad, dz, w, dx, store=getattr(geo, 'store', None))
+        dw = _wgrad_into(ctx.w_leaf, geo, dz, x, w) if geo.transposed else _wgrad_into(ctx.w_leaf, geo, x, dz, w)
+        return dx, dw, sums[:, 0], g[..., geo.Cout:], None
+
+
 class _ConvBiasSigmoid(torch.autograd.Function):
     """The prediction conv: normalizer_fn=None, biases, activation sigmoid (nets.py:139-155)."""
 
@@ -688,7 +730,7 @@ def _conv_layer_split(store, scope, x, cout, k, stride, reuse, transposed, defer
     return out if defer else out.materialize()
 
 
-def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer=False):
+def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer=False, cat_with=None):
     """conv / up-conv + batch-stat BN + ReLU.  `x` may be a pair (a, b) standing for tf.concat([a, b], axis=3): under
     no_grad the tensor-core kernel reads the two sources directly; with autograd the concat is materialised.
     Inference path (no_grad, tensor-core mode): the conv writes its RAW output and reduces the batch statistics in its
@@ -785,6 +827,14 @@ def _conv_layer(store, scope, x, cout, k, stride, reuse, transposed=False, defer
     w = store.get(scope + '/weights', geo.w_shape, reuse, 'weights')
     beta = store.get(scope + '/BatchNorm/beta', [cout], reuse, 'beta')
     geo.store = store
+    if (cat_with is not None and torch.is_grad_enabled() and _BN_BWD_FAST and _sync_bn_world()[1] == 1 and isinstance(cat_with, torch.Tensor)
+            and cat_with.is_cuda and cat_with.dtype == torch.float32 and cat_with.is_contiguous() and cat_with.dim() == 4
+            and tuple(cat_with.shape[:3]) == (B, geo.Ho, geo.Wo) and cout % 4 == 0 and cout <= 1024 and cat_with.shape[3] % 4 == 0):
+        # training path: this layer's output is only ever read as the first part of tf.concat([., cat_with], axis=3): build the concat
+        # directly (the caller recognises the tag and does not concatenate again)
+        out = _ConvBNReLUCat.apply(x, w, beta, cat_with, geo)
+        out._lsi_cat_done = True
+        return out
     y = _ConvBNReLU.apply(x, w, beta, geo)
     return y.half() if _f16_infer() else y       # (the 3-channel stem: fp32 CUDA-core conv, handed on as fp16)
 
@@ -803,9 +853,10 @@ def decoder_simple(feat, nconv=7, is_training=True, skip_feat=None, reuse=False,
         feat = feat[:, None, None, :]
     for nc in range(nconv, 0, -1):
         n_filt = n_filters[nc - 1]
-        feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True, defer=_defer)
-        if nc > 1 and skip_feat is not None:
-            feat = (feat, skip_feat[-nc + 1])                    # tf.concat([feat, skip], axis=3), nets.py:108-109
+        skip = skip_feat[-nc + 1] if (nc > 1 and skip_feat is not None) else None
+        feat = _conv_layer(store, '%s/upcnv%d' % (_scope, nc), feat, n_filt, 4, 2, reuse, transposed=True, defer=_defer, cat_with=skip)
+        if skip is not None and not getattr(feat, '_lsi_cat_done', False):
+            feat = (feat, skip)                                  # tf.concat([feat, skip], axis=3), nets.py:108-109
         feat = _conv_layer(store, '%s/upcnv%db' % (_scope, nc), feat, n_filt, 3, 1, reuse, defer=_defer)
         end_points['%s/upcnv%db' % (_scope, nc)] = feat
     return feat, end_points
@@ -956,8 +1007,9 @@ def encoder_decoder_unet(inp_img, nz=1000, is_training=True, reuse=False, nl_dif
     feats_dec = []
     feat = ep['cnv7b']
     for k, cout, skip in DEC[:7 - nl_diff_enc_dec]:
-        up = _conv_layer(store, '%s/upcnv%d' % (sc, k), feat, cout, 4, 2, reuse, transposed=True)
-        if skip is not None:
+        up = _conv_layer(store, '%s/upcnv%d' % (sc, k), feat, cout, 4, 2, reuse, transposed=True,
+                         cat_with=ep[skip] if skip is not None else None)
+        if skip is not None and not getattr(up, '_lsi_cat_done', False):
             up = (up, ep[skip])                                  # tf.concat([upcnv, skip], axis=3), nets.py:300,...
         feat = _conv_layer(store, '%s/icnv%d' % (sc, k), up, cout, 3, 1, reuse)
         ep['icnv%d' % k] = feat
