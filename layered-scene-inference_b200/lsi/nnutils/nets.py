@@ -474,6 +474,12 @@ def _sink_of(w):
     return w if (_GRAD_SINK[0] and w.is_leaf and w.grad is not None and w.grad.is_contiguous() and w.grad.dtype == torch.float32) else None
 
 
+def _dbeta_of(sums):
+    """dbeta = the first column of the (sum dz, sum dz*xhat) pairs: inside the trainer's gradient sink a strided view (autograd adds it to
+    the flat gradient buffer as it is -- no copy launch); a dense tensor for every other caller (e.g. one that all-reduces it)."""
+    return sums[:, 0] if _GRAD_SINK[0] else sums[:, 0].contiguous()
+
+
 def _wgrad_into(ctx_leaf, geo, big, small, like):
     """Weight gradient of one use of a filter: into the leaf's .grad (accumulating) when a sink is active, else a fresh tensor."""
     if ctx_leaf is not None and ctx_leaf.grad is not None:
@@ -537,12 +543,12 @@ class _ConvBNReLU(torch.autograd.Function):
             # dense fast path: reads z and dy only (ReLU mask recomputed from z exactly as the forward kernel evaluates it)
             _b200.call('lsi_b200_bn_relu_backward_z', _b200.ptr(z), _b200.ptr(beta), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
                        _b200.ptr(sums), P, geo.Cout, _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
-            dbeta = sums[:, 0]        # (a strided view: autograd accumulates it as it is -- no copy launch)
+            dbeta = _dbeta_of(sums)
         else:
             _b200.call('lsi_b200_bn_relu_backward', _b200.ptr(z), _b200.ptr(y), _b200.ptr(dy), _b200.ptr(stats), _b200.ptr(dz),
                        _b200.ptr(sums), P, geo.Cout, geo.Cout, geo.Cout, geo.Cout, geo.Cout, 1, 0,
                        _b200.ptr(_bn_workspace(dev, geo.Cout)), _b200.stream())
-            dbeta = sums[:, 0]        # (a strided view: autograd accumulates it as it is -- no copy launch)
+            dbeta = _dbeta_of(sums)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -590,7 +596,7 @@ class _ConvBNReLUCat(torch.autograd.Function):
             dx = torch.empty_like(x)
             _conv(geo.dgrad, dz, w, dx, store=getattr(geo, 'store', None))
         dw = _wgrad_into(ctx.w_leaf, geo, dz, x, w) if geo.transposed else _wgrad_into(ctx.w_leaf, geo, x, dz, w)
-        return dx, dw, sums[:, 0], g[..., geo.Cout:], None
+        return dx, dw, _dbeta_of(sums), g[..., geo.Cout:], None
 
 
 class _ConvBiasSigmoid(torch.autograd.Function):
@@ -619,7 +625,7 @@ class _ConvBiasSigmoid(torch.autograd.Function):
         dx = torch.empty_like(x)
         _conv(geo.dgrad, dz, w, dx, store=getattr(geo, 'store', None))
         dw = _wgrad_into(ctx.w_leaf, geo, x, dz, w)
-        return dx, dw, sums[:, 0], None
+        return dx, dw, _dbeta_of(sums), None
 
 
 class _ConcatChannels(torch.autograd.Function):
