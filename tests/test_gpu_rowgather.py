@@ -153,6 +153,23 @@ def test_rowgather_empty_rows_and_loud_misuse(mods):
     assert torch.isfinite(img[0, 0]).all() and torch.isnan(img[0, 1]).all() and torch.isnan(wts[0, 1]).all()
 
 
+def test_hint_on_a_shape_the_kernel_does_not_take(mods):
+    """Rows wider than 2048 pixels are outside the row-gather kernel; the all-rectified hint the mirror passes after the first sight of
+    the cameras must then fall back to the default path (streaming kernel), not fail."""
+    ldi, helpers = mods
+    L, B, H, W = 2, 1, 4, 2304
+    kw = dict(compose_layers=True, trg_downsampling=1, bg_layer_disp=1e-3, max_disp=0.4, zbuf_scale=50)
+    tex, mask, disp, k_s, k_t, rot, t = [x.cuda() for x in _scene(L, B, H, W, seed=31)]
+    pc = helpers.pixel_coords(B, H, W)
+    ref = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, _variant=1, **kw)
+    for it in range(3):
+        got = ldi.forward_splat((tex, mask, disp), pc, k_s, k_t, rot, t, **kw)
+        torch.cuda.synchronize()
+        for a, b in zip(got, ref):
+            assert torch.isfinite(a).all() and rel_err(a.cpu(), b.cpu()) < 2e-5
+    assert ldi._POSE_CACHE.lookup((k_s, k_t, rot, t))[1] == 'all'
+
+
 def test_no_image_in_class_hint(mods):
     """General poses for the whole batch: after the first sight the mirror passes variant 6 (no row-gather launch); same result."""
     ldi, helpers = mods
